@@ -1,0 +1,189 @@
+/* vlpk.h — C ABI of libvlpk.so, the B200-native (sm_100a) replacement for VLP's data-parallel hot path.
+ *
+ * The reference (LuoweiZhou/VLP) has no FFI layer: its operator API is the nn.Module surface of
+ * pytorch_pretrained_bert/modeling.py.  Each entry point below replaces the eager-PyTorch body of one of
+ * those modules (file:line cited per function); vlp_b200/vlp_modules.py keeps the Python surface and
+ * binds these symbols with ctypes (see INTEGRATION.md for the reference-side binding).
+ *
+ * Conventions
+ *   - every pointer is a raw CUDA device pointer owned by the caller; the library never allocates or
+ *     frees device memory and keeps no references after the call returns;
+ *   - activations / parameters are bf16, row-major; Linear weights are [out,in] exactly like nn.Linear;
+ *   - gradients of parameters are ACCUMULATED (+=) into caller-provided fp32 buffers (zero them first);
+ *   - `stream` is a cudaStream_t; all work is enqueued asynchronously on it, no host synchronisation,
+ *     CUDA-graph capturable;
+ *   - return value: 0 = OK, < 0 = argument/shape/alignment error (nothing launched),
+ *     > 0 = cudaError_t.  vlpk_last_error() returns a thread-local description.
+ *   - there is no CPU fallback and no other backend: unsupported configurations are errors.
+ */
+#ifndef VLPK_H_
+#define VLPK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLPK_VERSION 100
+
+/* dtype tags for vlpk_mask_pack */
+#define VLPK_BF16 0
+#define VLPK_F32 1
+#define VLPK_I64 2
+/* mask interpretation */
+#define VLPK_MASK_ADDITIVE 0 /* 0 / -10000 additive mask, modeling.py:832 */
+#define VLPK_MASK_ZERO_ONE 1 /* 1 = attend, 0 = masked, seq2seq_loader.py:291-304 */
+/* activations for vlpk_linear_* */
+#define VLPK_ACT_NONE 0
+#define VLPK_ACT_RELU 1
+
+typedef struct VlpkDropout {
+  float p;                  /* drop probability; 0 disables */
+  uint64_t seed;            /* Philox key */
+  const uint64_t* seed_dev; /* optional device counter added to `seed` at run time (CUDA-graph replays) */
+} VlpkDropout;
+
+typedef struct VlpkShape {
+  int32_t B;     /* sequences */
+  int32_t Lq;    /* query rows per sequence  (<= 128) */
+  int32_t Lkv;   /* key/value rows per sequence (<= 128); == Lq except incremental decode */
+  int32_t H;     /* hidden size (multiple of 64) */
+  int32_t heads; /* H / 64 */
+  int32_t I;     /* intermediate size */
+} VlpkShape;
+
+/* One BertLayer's parameters (modeling.py:244-372), bf16, nn.Linear layout [out,in]. */
+typedef struct VlpkLayerWeights {
+  const void *wq, *wk, *wv; /* attention.self.{query,key,value}.weight [H,H] */
+  const void *bq, *bk, *bv; /* .bias [H] */
+  const void *wo, *bo;      /* attention.output.dense [H,H],[H] */
+  const void *ln1_g, *ln1_b;/* attention.output.LayerNorm */
+  const void *w1, *b1;      /* intermediate.dense [I,H],[I] */
+  const void *w2, *b2;      /* output.dense [H,I],[H] */
+  const void *ln2_g, *ln2_b;/* output.LayerNorm */
+} VlpkLayerWeights;
+
+/* fp32 gradient accumulators for one layer. */
+typedef struct VlpkLayerGrads {
+  float* wqkv; /* [3H,H] rows = query | key | value */
+  float* bqkv; /* [3H] */
+  float *wo, *bo, *ln1_g, *ln1_b, *w1, *b1, *w2, *b2, *ln2_g, *ln2_b;
+} VlpkLayerGrads;
+
+/* Per-layer activations written by forward and read by backward (all caller-allocated). */
+typedef struct VlpkLayerActs {
+  void* qkv;     /* [B*Lq, 3H]  (incremental decode: q in [:, :H] of a [B*Lq,H] buffer — see vlpk_mha_fwd) */
+  void* ctx;     /* [B*Lq, H]   attention context */
+  void* t1;      /* [B*Lq, H]   attention.output.dense result */
+  void* y1;      /* [B*Lq, H]   BertAttention output (after LayerNorm) */
+  void* u;       /* [B*Lq, I]   pre-GELU */
+  void* hmid;    /* [B*Lq, I]   GELU output */
+  void* t2;      /* [B*Lq, H]   output.dense result */
+  void* y;       /* [B*Lq, H]   layer output */
+  float* lse;    /* [B, heads, Lq] */
+  float* stats1; /* [B*Lq, 2]  (mean, rstd) of attention.output.LayerNorm */
+  float* stats2; /* [B*Lq, 2] */
+  void* kv;      /* incremental decode only: [B*Lkv, 2H] key|value projections; else NULL */
+} VlpkLayerActs;
+
+/* Scratch for backward, shared by all layers (bf16). */
+typedef struct VlpkBwdScratch {
+  void* dz2;  /* [M,H] */
+  void* dt2;  /* [M,H] */
+  void* du;   /* [M,I] */
+  void* dy1;  /* [M,H] */
+  void* dz1;  /* [M,H] */
+  void* dt1;  /* [M,H] */
+  void* dctx; /* [M,H] */
+  void* dqkv; /* [M,3H] */
+  void* dx;   /* [M,H] ping-pong buffer for the inter-layer gradient */
+} VlpkBwdScratch;
+
+int vlpk_version(void);
+const char* vlpk_last_error(void);
+/* bring-up only: override the MN-major UMMA descriptor geometry used by vlpk_gemm (defaults 8192,1024,2048). */
+void vlpk_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep);
+
+/* get_extended_attention_mask (modeling.py:807-833) -> per-row 128-bit "attend" bitmask.
+ * mask: [B, rows, kv] with element strides (stride_b, stride_r, 1); rows may be 1 (2-D mask). out: [B, rows, 4] u32. */
+int vlpk_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, int64_t stride_b, int64_t stride_r,
+                   uint32_t* out, void* stream);
+
+/* y[M,N] = dropout(act(x[M,K] w[N,K]^T + b)) — vis_embed / vis_pe_embed Linears (modeling.py:1003-1018, 1035-1036).
+ * K need not be tile aligned but ldx/ldw (elements) must be multiples of 8. */
+int vlpk_linear_fwd(int M, int N, int K, const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias, void* y,
+                    int64_t ldy, int act, const VlpkDropout* drop, uint64_t site, void* stream);
+/* Backward of the above.  dy is the gradient of y; y is the forward output (ReLU/dropout mask is recovered from y>0).
+ * dpre: [M,N] bf16 scratch (gradient before activation).  dx may be NULL.  dw [N,ldw_g] / db [N] fp32, accumulated. */
+int vlpk_linear_bwd(int M, int N, int K, const void* x, int64_t ldx, const void* w, int64_t ldw, const void* y, int64_t ldy,
+                    const void* dy, int64_t lddy, void* dpre, void* dx, int64_t lddx, float* dw, int64_t lddw, float* db,
+                    int act, float p_drop, void* stream);
+
+/* BertEmbeddings.forward (modeling.py:217-241): gathers + region splice + LayerNorm(eps 1e-5) + dropout. */
+int vlpk_embed_fwd(int B, int L, int H, int R, int vis_input, const int64_t* ids, const int64_t* token_type, const int64_t* pos,
+                   const void* word_w, const void* pos_w, const void* type_w, const void* vis, const void* vis_pe,
+                   const void* ln_g, const void* ln_b, void* y, float* stats, const VlpkDropout* drop, uint64_t site, void* stream);
+/* dz = gradient wrt the pre-LayerNorm sum [B*L,H] (caller scatters it to tables / region projections). */
+int vlpk_embed_bwd(int B, int L, int H, int R, int vis_input, const int64_t* ids, const int64_t* token_type, const int64_t* pos,
+                   const void* word_w, const void* pos_w, const void* type_w, const void* vis, const void* vis_pe,
+                   const void* ln_g, const float* stats, const void* dy, void* dz, float* d_ln_g, float* d_ln_b,
+                   const VlpkDropout* drop, uint64_t site, void* stream);
+
+/* y = LayerNorm(dropout(t) + res) (BertSelfOutput / BertOutput tail, modeling.py:315-316, 355-356; eps 1e-5). */
+int vlpk_ln_res_drop_fwd(int64_t M, int H, const void* t, const void* res, const void* gamma, const void* beta, void* y,
+                         float* stats, const VlpkDropout* drop, uint64_t site, void* stream);
+int vlpk_ln_res_drop_bwd(int64_t M, int H, const void* t, const void* res, const void* gamma, const float* stats, const void* dy,
+                         void* dz, void* dt, float* dgamma, float* dbeta, float* dbias, const VlpkDropout* drop, uint64_t site,
+                         void* stream);
+
+/* softmax(QK^T/8 + mask) V per (sequence, head) — BertSelfAttention core (modeling.py:279-302). */
+int vlpk_attn_core_fwd(int B, int heads, int Lq, int Lkv, const void* q, int64_t ld_q, const void* k, const void* v, int64_t ld_kv,
+                       const uint32_t* mask_bits, int mask_rows, void* ctx, int64_t ld_ctx, float* lse, const VlpkDropout* drop,
+                       uint64_t site, void* stream);
+int vlpk_attn_core_bwd(int B, int heads, int L, const void* q, const void* k, const void* v, int64_t ld_qkv, const uint32_t* mask_bits,
+                       int mask_rows, const void* ctx, const void* dctx, int64_t ld_ctx, const float* lse, void* dq, void* dk,
+                       void* dv, int64_t ld_dqkv, const VlpkDropout* drop, uint64_t site, void* stream);
+
+/* BertAttention.forward (modeling.py:326-330): QKV projection + attention core + output projection + LN.
+ * x_kv == NULL or == x: self-attention over x (training / encoder path).
+ * x_kv != x: incremental decode (modeling.py:273-277): keys/values projected from x_kv = cat(history, x), [B*Lkv,H]. */
+int vlpk_mha_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* mask_bits,
+                 int mask_rows, VlpkLayerActs* a, float p_attn, float p_hidden, const VlpkDropout* drop, uint64_t layer_id,
+                 void* stream);
+/* BertIntermediate + BertOutput (modeling.py:340-343, 353-357): y = LN(dropout(gelu(y1 W1^T+b1) W2^T + b2) + y1). */
+int vlpk_ffn_fwd(const VlpkShape* s, const VlpkLayerWeights* w, VlpkLayerActs* a, float p_hidden, const VlpkDropout* drop,
+                 uint64_t layer_id, void* stream);
+/* BertLayer.forward (modeling.py:367-372) = mha + ffn. */
+int vlpk_layer_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* mask_bits,
+                   int mask_rows, VlpkLayerActs* a, float p_attn, float p_hidden, const VlpkDropout* drop, uint64_t layer_id,
+                   void* stream);
+/* Backward of BertLayer: dy = gradient of a->y; writes dx (gradient of x); accumulates parameter gradients. */
+int vlpk_layer_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits, int mask_rows,
+                   const VlpkLayerActs* a, const void* dy, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws,
+                   float p_attn, float p_hidden, const VlpkDropout* drop, uint64_t layer_id, void* stream);
+
+/* BertEncoder.forward (modeling.py:382-402): n_layers x BertLayer in one host call.  acts[i].y is layer i's output. */
+int vlpk_encoder_fwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits,
+                     int mask_rows, VlpkLayerActs* acts, float p_attn, float p_hidden, const VlpkDropout* drop, void* stream);
+/* Backward of the stack.  dys[i] (may be NULL) is the gradient flowing into layer i's output from outside the stack
+ * (output_all_encoded_layers consumers); dys[n_layers-1] is normally the only non-NULL entry.  dx0 receives d/dx. */
+int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits,
+                     int mask_rows, const VlpkLayerActs* acts, const void* const* dys, void* dx0, const VlpkLayerGrads* grads,
+                     const VlpkBwdScratch* ws, float p_attn, float p_hidden, const VlpkDropout* drop, void* stream);
+
+/* utilities */
+int vlpk_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+int vlpk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, void* stream);
+int vlpk_add_bf16(void* dst, const void* a, const void* b, int64_t n, void* stream);
+
+/* Raw GEMM building block (exposed for tests / bring-up).  D[M,N] = sum_k A[m,k] B[n,k].
+ * a_mn / b_mn: operand stored with the M (resp. N) index contiguous instead of k.  epi: see csrc/gemm.cuh. */
+int vlpk_gemm(int M, int N, int K, int a_mn, const void* A, int64_t lda, int b_mn, const void* B, int64_t ldb, const void* bias,
+              void* D0, int64_t ldd0, void* D1, int64_t ldd1, const void* aux, int64_t ld_aux, int epi, int splits, int bn,
+              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLPK_H_ */

@@ -1,0 +1,507 @@
+// vlp_b200 — masked-softmax attention core for VLP's [image-region | text-token] sequence (L <= 128).
+//
+// Reference semantics (pytorch_pretrained_bert/modeling.py:279-302):
+//   S = Q K^T / sqrt(64) + mask_add ; P = softmax(S) ; P = dropout(P) ; ctx = P V
+// where mask_add is 0 / -10000 (modeling.py:832).  One whole sequence (123 -> 128 rows) is a single
+// 128-row UMMA tile, so S and P live only in TMEM / registers / shared memory: the reference's
+// [B,12,L,L] score tensor (written + read ~6x per layer) never touches HBM.
+//
+// One CTA per (head, batch).  4 warps; thread t owns row t of the tile (tcgen05.ld 32x32b layout).
+//   fwd : TMA Q,K,V -> S=QK^T (tcgen05, TMEM) -> scale+bitmask+softmax in registers -> Philox dropout
+//         -> P (bf16, swizzled smem) -> O=PV (tcgen05, V read MN-major straight from its [kv,d] tile)
+//         -> O/rowsum -> TMA store.  Saves only logsumexp per row for backward.
+//   bwd : recompute S,P from Q,K + logsumexp; dP=dO V^T; dS=P*(dP-delta)/8; dV=P^T dO; dK=dS^T Q; dQ=dS K
+//         — five UMMAs, all operands fed from the same five TMA tiles via K-major / MN-major descriptors.
+#include "attn.cuh"
+#include "host.cuh"
+
+namespace vlpk {
+
+static constexpr int HD = 64;         // head dim (VLP/BERT-base: 768/12)
+static constexpr int TL = 128;        // tile rows (max sequence length)
+static constexpr int TILE_B = TL * 128;  // bytes of one [128 x 64] bf16 tile
+static constexpr float LOG2E = 1.4426950408889634f;
+static constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnTmaps {
+  CUtensorMap q, k, v, o;         // fwd: o = ctx ; bwd: o = dO (load)
+  CUtensorMap dq, dk, dv;         // bwd outputs
+};
+
+struct AttnArgs {
+  int B, heads, Lq, Lkv;
+  const uint32_t* mask_bits;  // [B, mask_rows, 4] ; bit j of row i set = attend to kv position j
+  int mask_rows;              // Lq, or 1 when the mask broadcasts over query rows
+  float* lse;                 // [B, heads, Lq] natural-log logsumexp of the scaled+masked scores
+  const __nv_bfloat16* o_ptr;   // bwd: forward output ctx [B, Lq, ld_o] (for delta)
+  const __nv_bfloat16* do_ptr;  // bwd: dO, same layout
+  long long ld_o;
+  DropoutCfg drop;
+};
+
+__device__ __forceinline__ void sw_write16(uint8_t* tile, int row, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+}
+
+// Scaled + masked score in the log2 domain for 32 columns starting at col0.
+// bit set -> attend (add 0) ; bit clear -> add -10000 (reference additive mask) ; col >= Lkv -> -inf.
+__device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], uint32_t mbits, int col0, int Lkv, float (&t)[32]) {
+  const float sc = 0.125f * LOG2E;
+  const float neg = -10000.0f * LOG2E;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(r[j]) * sc + (((mbits >> j) & 1u) ? 0.f : neg);
+    t[j] = (col0 + j < Lkv) ? x : -INFINITY;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct FwdSmem {
+  static constexpr int OFF_Q = 0;                 // also O staging
+  static constexpr int OFF_K = TILE_B;
+  static constexpr int OFF_V = 2 * TILE_B;
+  static constexpr int OFF_P = 3 * TILE_B;        // 2 atoms x 16 KB
+  static constexpr int OFF_BAR = 5 * TILE_B;
+  static constexpr int TOTAL = OFF_BAR + 64;
+  static constexpr int DYN = TOTAL + 1024;
+};
+
+__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + FwdSmem::OFF_Q;
+  uint8_t* sK = smem + FwdSmem::OFF_K;
+  uint8_t* sV = smem + FwdSmem::OFF_V;
+  uint8_t* sP = smem + FwdSmem::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::OFF_BAR);
+  uint64_t* bar_qk = &bars[0];
+  uint64_t* bar_v = &bars[1];
+  uint64_t* bar_s = &bars[2];
+  uint64_t* bar_o = &bars[3];
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid;
+  const uint64_t dseed = drop_seed(a.drop);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm.q);
+    tma_prefetch_desc(&tm.k);
+    tma_prefetch_desc(&tm.v);
+    mbar_init(bar_qk, 1);
+    mbar_init(bar_v, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_qk, 2 * TILE_B);
+    tma_load_3d(sQ, &tm.q, bar_qk, h * HD, 0, b);
+    tma_load_3d(sK, &tm.k, bar_qk, h * HD, 0, b);
+    mbar_arrive_expect_tx(bar_v, TILE_B);
+    tma_load_3d(sV, &tm.v, bar_v, h * HD, 0, b);
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      umma_f16(tS, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+               umma_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+
+  // mask bits for this query row
+  uint32_t mb[4] = {0, 0, 0, 0};
+  {
+    const int mr = (a.mask_rows == 1) ? 0 : min(row, a.mask_rows - 1);
+    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4));
+    mb[0] = m4.x; mb[1] = m4.y; mb[2] = m4.z; mb[3] = m4.w;
+  }
+
+  mbar_wait(bar_s, 0);
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+
+  // pass 1: row max (log2 domain)
+  float tmax = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    float t[32];
+    tmem_ld32(tS + t_lane + c * 32, r);
+    tmem_ld_wait();
+    score_chunk(r, mb[c], c * 32, a.Lkv, t);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, t[j]);
+  }
+  // pass 2: exponentiate, row sum, dropout, write un-normalised P (bf16) as the A operand of P·V
+  float rsum = 0.f;
+  const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + row) * TL;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32];
+    float t[32];
+    tmem_ld32(tS + t_lane + c * 32, r);
+    tmem_ld_wait();
+    score_chunk(r, mb[c], c * 32, a.Lkv, t);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t keep = 0xFFu;
+      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float e0 = exp2f(t[g * 8 + 2 * j] - tmax);
+        const float e1 = exp2f(t[g * 8 + 2 * j + 1] - tmax);
+        rsum += e0 + e1;
+        const float p0 = ((keep >> (2 * j)) & 1u) ? e0 * a.drop.scale : 0.f;
+        const float p1 = ((keep >> (2 * j + 1)) & 1u) ? e1 * a.drop.scale : 0.f;
+        pk[j] = pack_bf16x2(p0, p1);
+      }
+      const int col = c * 32 + g * 8;
+      sw_write16(sP + (col >> 6) * TILE_B, row, (col & 63) >> 3, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
+#pragma unroll
+    for (int k = 0; k < TL / 16; ++k)
+      umma_f16(tO, umma_smem_desc_sw128(smem_u32(sP) + (k >> 2) * TILE_B + (k & 3) * 32, 16, 1024),
+               umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+    umma_commit(bar_o);
+  }
+  if (a.lse != nullptr && row < a.Lq)
+    a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] = (tmax + log2f(rsum)) * LN2;
+
+  mbar_wait(bar_o, 0);
+  __syncwarp();
+  tc_fence_after();
+  const float inv = 1.0f / rsum;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tO + t_lane + c * 32, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        pk[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]) * inv, __uint_as_float(r[g * 8 + 2 * j + 1]) * inv);
+      sw_write16(sQ, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));  // Q tile is dead: reuse as staging
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&tm.o, sQ, h * HD, 0, b);
+    tma_store_commit();
+    tma_store_wait<0>();
+  }
+  tc_fence_after();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc<256>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+struct BwdSmem {
+  static constexpr int OFF_Q = 0;            // later dQ staging
+  static constexpr int OFF_K = TILE_B;       // later dK staging
+  static constexpr int OFF_V = 2 * TILE_B;   // later dV staging
+  static constexpr int OFF_DO = 3 * TILE_B;
+  static constexpr int OFF_P = 4 * TILE_B;   // 2 atoms
+  static constexpr int OFF_DS = 6 * TILE_B;  // 2 atoms
+  static constexpr int OFF_BAR = 8 * TILE_B;
+  static constexpr int TOTAL = OFF_BAR + 64;
+  static constexpr int DYN = TOTAL + 1024;
+};
+
+__global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + BwdSmem::OFF_Q;
+  uint8_t* sK = smem + BwdSmem::OFF_K;
+  uint8_t* sV = smem + BwdSmem::OFF_V;
+  uint8_t* sdO = smem + BwdSmem::OFF_DO;
+  uint8_t* sP = smem + BwdSmem::OFF_P;
+  uint8_t* sdS = smem + BwdSmem::OFF_DS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::OFF_BAR);
+  uint64_t* bar_in = &bars[0];
+  uint64_t* bar_s = &bars[1];
+  uint64_t* bar_o = &bars[2];
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[3]);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid;
+  const uint64_t dseed = drop_seed(a.drop);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm.q);
+    tma_prefetch_desc(&tm.k);
+    tma_prefetch_desc(&tm.v);
+    tma_prefetch_desc(&tm.o);
+    mbar_init(bar_in, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(bar_in, 4 * TILE_B);
+    tma_load_3d(sQ, &tm.q, bar_in, h * HD, 0, b);
+    tma_load_3d(sK, &tm.k, bar_in, h * HD, 0, b);
+    tma_load_3d(sV, &tm.v, bar_in, h * HD, 0, b);
+    tma_load_3d(sdO, &tm.o, bar_in, h * HD, 0, b);
+    mbar_wait(bar_in, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 128, false, false);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      umma_f16(tS, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+               umma_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k)
+      umma_f16(tdP, umma_smem_desc_sw128(smem_u32(sdO) + k * 32, 16, 1024),
+               umma_smem_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc, k > 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+
+  const bool row_ok = row < a.Lq;
+  uint32_t mb[4] = {0, 0, 0, 0};
+  {
+    const int mr = (a.mask_rows == 1) ? 0 : min(row, a.mask_rows - 1);
+    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4));
+    mb[0] = m4.x; mb[1] = m4.y; mb[2] = m4.z; mb[3] = m4.w;
+  }
+  // delta_r = sum_d dO[r,d] * O[r,d]  (= sum_j P_rj dP_rj, the softmax-backward row term)
+  float delta = 0.f, lse2 = 0.f;
+  if (row_ok) {
+    const size_t off = (static_cast<size_t>(b) * a.Lq + row) * a.ld_o + h * HD;
+    const uint4* po = reinterpret_cast<const uint4*>(a.o_ptr + off);
+    const uint4* pd = reinterpret_cast<const uint4*>(a.do_ptr + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 x = __ldg(po + i), y = __ldg(pd + i);
+      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 xf = unpack_bf16x2(xw[j]), yf = unpack_bf16x2(yw[j]);
+        delta += xf.x * yf.x + xf.y * yf.y;
+      }
+    }
+    lse2 = a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] * LOG2E;
+  }
+
+  mbar_wait(bar_s, 0);
+  __syncwarp();
+  tc_fence_after();
+  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+  const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + row) * TL;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t r[32], d[32];
+    float t[32];
+    tmem_ld32(tS + t_lane + c * 32, r);
+    tmem_ld32(tdP + t_lane + c * 32, d);
+    tmem_ld_wait();
+    score_chunk(r, mb[c], c * 32, a.Lkv, t);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t keep = 0xFFu;
+      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+      uint32_t pk[4], dk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float pv[2], dv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int jj = g * 8 + 2 * j + e;
+          const float p = row_ok ? exp2f(t[jj] - lse2) : 0.f;  // exp2(-inf) = 0 for columns >= Lkv
+          const bool kp = (keep >> (2 * j + e)) & 1u;
+          const float dpm = kp ? __uint_as_float(d[jj]) * a.drop.scale : 0.f;
+          pv[e] = kp ? p * a.drop.scale : 0.f;
+          dv[e] = p * (dpm - delta) * 0.125f;
+        }
+        pk[j] = pack_bf16x2(pv[0], pv[1]);
+        dk[j] = pack_bf16x2(dv[0], dv[1]);
+      }
+      const int col = c * 32 + g * 8;
+      sw_write16(sP + (col >> 6) * TILE_B, row, (col & 63) >> 3, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      sw_write16(sdS + (col >> 6) * TILE_B, row, (col & 63) >> 3, make_uint4(dk[0], dk[1], dk[2], dk[3]));
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc_mm = umma_idesc_bf16(128, HD, true, true);   // A^T from [q,kv] tile, B from [q,d] tile
+    constexpr uint32_t idesc_km = umma_idesc_bf16(128, HD, false, true);  // A = dS [q,kv], B from [kv,d] tile
+#pragma unroll
+    for (int k = 0; k < TL / 16; ++k)  // dV[kv,d] = sum_q Pd[q,kv] dO[q,d]
+      umma_f16(tdV, umma_smem_desc_sw128(smem_u32(sP) + k * 2048, TILE_B, 1024),
+               umma_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_mm, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < TL / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d]
+      umma_f16(tdK, umma_smem_desc_sw128(smem_u32(sdS) + k * 2048, TILE_B, 1024),
+               umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_mm, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < TL / 16; ++k)  // dQ[q,d] = sum_kv dS[q,kv] K[kv,d]
+      umma_f16(tdQ, umma_smem_desc_sw128(smem_u32(sdS) + (k >> 2) * TILE_B + (k & 3) * 32, 16, 1024),
+               umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_km, k > 0 ? 1u : 0u);
+    umma_commit(bar_o);
+  }
+  mbar_wait(bar_o, 0);
+  __syncwarp();
+  tc_fence_after();
+  // all MMAs retired: Q/K/V tiles are dead, reuse them as output staging
+#pragma unroll 1
+  for (int o = 0; o < 3; ++o) {
+    const uint32_t tsrc = (o == 0) ? tdQ : (o == 1 ? tdK : tdV);
+    uint8_t* stg = (o == 0) ? sQ : (o == 1 ? sK : sV);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tsrc + t_lane + c * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          pk[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+        sw_write16(stg, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&tm.dq, sQ, h * HD, 0, b);
+    tma_store_3d(&tm.dk, sK, h * HD, 0, b);
+    tma_store_3d(&tm.dv, sV, h * HD, 0, b);
+    tma_store_commit();
+    tma_store_wait<0>();
+  }
+  tc_fence_after();
+  if (warp == 0) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int make_seq_tmap(CUtensorMap* out, const void* base, int width, int L, int B, int64_t ld) {
+  uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
+  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(L)};
+  uint32_t box[3] = {HD, TL, 1};
+  return make_tmap(out, TM_BF16, 3, base, dims, strides, box);
+}
+
+static int check_common(const AttnDesc& d) {
+  VLPK_CHECK_ARG(d.head_dim == HD, "attention: head_dim %d unsupported (only 64)", d.head_dim);
+  VLPK_CHECK_ARG(d.Lq >= 1 && d.Lq <= TL && d.Lkv >= 1 && d.Lkv <= TL, "attention: Lq=%d Lkv=%d must be in [1,128]",
+                 d.Lq, d.Lkv);
+  VLPK_CHECK_ARG(d.B >= 1 && d.heads >= 1, "attention: B=%d heads=%d", d.B, d.heads);
+  VLPK_CHECK_ARG(d.mask_bits != nullptr && (d.mask_rows == 1 || d.mask_rows == d.Lq), "attention: mask rows %d",
+                 d.mask_rows);
+  return 0;
+}
+
+int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
+  VLPK_TRY(check_common(d));
+  const int width = d.heads * HD;
+  AttnTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  VLPK_TRY(make_seq_tmap(&tm.q, d.q, width, d.Lq, d.B, d.ld_q));
+  VLPK_TRY(make_seq_tmap(&tm.k, d.k, width, d.Lkv, d.B, d.ld_kv));
+  VLPK_TRY(make_seq_tmap(&tm.v, d.v, width, d.Lkv, d.B, d.ld_kv));
+  VLPK_TRY(make_seq_tmap(&tm.o, d.o, width, d.Lq, d.B, d.ld_o));
+  tm.dq = tm.dk = tm.dv = tm.o;
+  AttnArgs a;
+  a.B = d.B; a.heads = d.heads; a.Lq = d.Lq; a.Lkv = d.Lkv;
+  a.mask_bits = d.mask_bits; a.mask_rows = d.mask_rows;
+  a.lse = d.lse; a.o_ptr = nullptr; a.do_ptr = nullptr; a.ld_o = d.ld_o;
+  a.drop = d.drop;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLPK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::DYN));
+    attr_set = true;
+  }
+  attn_fwd_kernel<<<dim3(d.heads, d.B), 128, FwdSmem::DYN, stream>>>(tm, a);
+  VLPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_attn_bwd(const AttnDesc& d, cudaStream_t stream) {
+  VLPK_TRY(check_common(d));
+  VLPK_CHECK_ARG(d.Lq == d.Lkv, "attention bwd: Lq must equal Lkv (training path)");
+  VLPK_CHECK_ARG(d.lse != nullptr && d.d_o != nullptr && d.dq && d.dk && d.dv, "attention bwd: missing buffers");
+  const int width = d.heads * HD;
+  AttnTmaps tm;
+  memset(&tm, 0, sizeof(tm));
+  VLPK_TRY(make_seq_tmap(&tm.q, d.q, width, d.Lq, d.B, d.ld_q));
+  VLPK_TRY(make_seq_tmap(&tm.k, d.k, width, d.Lkv, d.B, d.ld_kv));
+  VLPK_TRY(make_seq_tmap(&tm.v, d.v, width, d.Lkv, d.B, d.ld_kv));
+  VLPK_TRY(make_seq_tmap(&tm.o, d.d_o, width, d.Lq, d.B, d.ld_o));
+  VLPK_TRY(make_seq_tmap(&tm.dq, d.dq, width, d.Lq, d.B, d.ld_dqkv));
+  VLPK_TRY(make_seq_tmap(&tm.dk, d.dk, width, d.Lkv, d.B, d.ld_dqkv));
+  VLPK_TRY(make_seq_tmap(&tm.dv, d.dv, width, d.Lkv, d.B, d.ld_dqkv));
+  AttnArgs a;
+  a.B = d.B; a.heads = d.heads; a.Lq = d.Lq; a.Lkv = d.Lkv;
+  a.mask_bits = d.mask_bits; a.mask_rows = d.mask_rows;
+  a.lse = d.lse;
+  a.o_ptr = reinterpret_cast<const __nv_bfloat16*>(d.o);
+  a.do_ptr = reinterpret_cast<const __nv_bfloat16*>(d.d_o);
+  a.ld_o = d.ld_o;
+  a.drop = d.drop;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VLPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::DYN));
+    attr_set = true;
+  }
+  attn_bwd_kernel<<<dim3(d.heads, d.B), 128, BwdSmem::DYN, stream>>>(tm, a);
+  VLPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vlpk

@@ -1,0 +1,58 @@
+// vlp_b200 — host-side utilities: error channel, TMA descriptor encode, device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace vlpk {
+
+// Thread-local last-error text surfaced through vlpk_last_error() (include/vlpk.h).
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define VLPK_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::vlpk::set_error(__VA_ARGS__);      \
+      return -1;                           \
+    }                                      \
+  } while (0)
+
+#define VLPK_CUDA(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::vlpk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return static_cast<int>(_e);                                                             \
+    }                                                                                          \
+  } while (0)
+
+#define VLPK_TRY(expr)        \
+  do {                        \
+    int _rc = (expr);         \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+enum TmapDtype { TM_BF16 = 0, TM_F32 = 1 };
+
+// Encode a tiled tensor map with 128-byte swizzle over a row-major tensor of `rank` dims.
+// dims[0] is the contiguous dimension.  strides_bytes[i] is the byte stride of dims[i+1].
+// Out-of-bounds box elements are zero-filled on load and clipped on store.
+int make_tmap(CUtensorMap* out, TmapDtype dt, int rank, const void* base, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
+
+inline int make_tmap_2d(CUtensorMap* out, TmapDtype dt, const void* base, uint64_t inner, uint64_t outer,
+                        uint64_t ld_elems, uint32_t box_inner, uint32_t box_outer) {
+  const uint64_t es = (dt == TM_BF16) ? 2 : 4;
+  uint64_t dims[2] = {inner, outer};
+  uint64_t strides[1] = {ld_elems * es};
+  uint32_t box[2] = {box_inner, box_outer};
+  return make_tmap(out, dt, 2, base, dims, strides, box);
+}
+
+int num_sms();
+
+}  // namespace vlpk
