@@ -172,6 +172,15 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
                      int mask_rows, const VlpkLayerActs* acts, const void* const* dys, void* dx0, const VlpkLayerGrads* grads,
                      const VlpkBwdScratch* ws, float p_attn, float p_hidden, const VlpkDropout* drop, void* stream);
 
+/* Launch accounting.  vlpk_launch_count: kernels launched by this library in this process.  With profiling enabled every
+ * launch is bracketed by CUDA events on its stream; vlpk_profile_get sums device time (ms), algorithmic work (FLOPs for the
+ * tensor-core kernels, HBM bytes for the bandwidth kernels) and launches of one kernel family since the last reset.
+ * Families: 0 gemm fwd, 1 gemm dgrad, 2 gemm wgrad, 3 attention fwd, 4 attention bwd, 5 LN fwd, 6 LN bwd, 7 embed, 8 misc. */
+void vlpk_profile_enable(int on);
+void vlpk_profile_reset(void);
+int vlpk_profile_get(int cat, double* ms, double* work, int64_t* launches);
+int64_t vlpk_launch_count(void);
+
 /* utilities */
 int vlpk_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int vlpk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, void* stream);

@@ -1,0 +1,12 @@
+"""Kernel-level parity (GPU): each kernel family of libvlpk.so, called through the C ABI, against plain PyTorch fp32 math of
+the same op at small and production tile shapes (cases live in tools/bringup.py so they can also run as a harness)."""
+import pytest
+
+from tools import bringup
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", ["gemm_kk", "gemm_epi", "gemm_dgrad", "gemm_wgrad", "attn", "rowops"])
+def test_kernel_family(case):
+    assert bringup.CASES[case]()

@@ -80,6 +80,10 @@ _SIGS = {
     "vlpk_encoder_bwd": (c_int, [C.POINTER(VlpkShape), c_int, C.POINTER(VlpkLayerWeights), _P, _P, c_int,
                                  C.POINTER(VlpkLayerActs), C.POINTER(c_void_p), _P, C.POINTER(VlpkLayerGrads),
                                  C.POINTER(VlpkBwdScratch), c_float, c_float, C.POINTER(VlpkDropout), _P]),
+    "vlpk_profile_enable": (None, [c_int]),
+    "vlpk_profile_reset": (None, []),
+    "vlpk_profile_get": (c_int, [c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_i64)]),
+    "vlpk_launch_count": (c_i64, []),
     "vlpk_f32_to_bf16": (c_int, [_P, _P, c_i64, _P]),
     "vlpk_colsum": (c_int, [_P, c_i64, c_i64, c_int, _P, _P]),
     "vlpk_add_bf16": (c_int, [_P, _P, _P, c_i64, _P]),

@@ -291,6 +291,7 @@ int vlpk_linear_bwd(int M, int N, int K, const void* x, int64_t ldx, const void*
   if (act == VLPK_ACT_RELU) {
     VLPK_CHECK_ARG(y != nullptr && dpre != nullptr && N % 8 == 0, "linear_bwd: relu needs y, dpre and N %% 8 == 0");
     const long long n = static_cast<long long>(M) * N;
+    LaunchScope scope(CAT_MISC, 6.0 * n, st);
     relu_bwd_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, st>>>(static_cast<bf16*>(dpre), static_cast<const bf16*>(dy),
                                                                              static_cast<const bf16*>(y), M, N, lddy, ldy,
                                                                              p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f);
@@ -459,6 +460,7 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
     const void* xin = (i == 0) ? x : acts[i - 1].y;
     VLPK_TRY(layer_bwd_impl(s, &w[i], xin, mask_bits, mask_rows, &acts[i], cur_dy, out, &grads[i], ws, p_attn, p_hidden, drop, i, st));
     if (i > 0 && dys[i - 1] != nullptr) {
+      LaunchScope scope(CAT_MISC, 6.0 * n, st);
       add_bf16_kernel<<<static_cast<unsigned>(((n + 7) / 8 + 255) / 256), 256, 0, st>>>(static_cast<bf16*>(out), static_cast<const bf16*>(out),
                                                                                      static_cast<const bf16*>(dys[i - 1]), n);
       VLPK_CUDA(cudaGetLastError());
@@ -467,6 +469,16 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
   }
   return 0;
 }
+
+void vlpk_profile_enable(int on) { prof_enable(on != 0); }
+void vlpk_profile_reset(void) { prof_reset(); }
+int vlpk_profile_get(int cat, double* ms, double* work, int64_t* launches) {
+  long long n = 0;
+  const int rc = prof_get(cat, ms, work, &n);
+  *launches = n;
+  return rc;
+}
+int64_t vlpk_launch_count(void) { return launch_count(); }
 
 int vlpk_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) { return launch_f32_to_bf16(src, dst, n, S(stream)); }
 
@@ -478,6 +490,7 @@ int vlpk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, void* s
 int vlpk_add_bf16(void* dst, const void* a, const void* b, int64_t n, void* stream) {
   VLPK_CHECK_ARG(dst && a && b, "add_bf16: null pointer");
   if (n <= 0) return 0;
+  LaunchScope scope(CAT_MISC, 6.0 * n, S(stream));
   add_bf16_kernel<<<static_cast<unsigned>(((n + 7) / 8 + 255) / 256), 256, 0, S(stream)>>>(static_cast<bf16*>(dst), static_cast<const bf16*>(a),
                                                                                         static_cast<const bf16*>(b), n);
   VLPK_CUDA(cudaGetLastError());

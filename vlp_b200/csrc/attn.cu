@@ -467,6 +467,7 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     VLPK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::DYN));
     attr_set = true;
   }
+  LaunchScope scope(CAT_ATTN_FWD, 4.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
   attn_fwd_kernel<<<dim3(d.heads, d.B), 128, FwdSmem::DYN, stream>>>(tm, a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
@@ -499,6 +500,7 @@ int launch_attn_bwd(const AttnDesc& d, cudaStream_t stream) {
     VLPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::DYN));
     attr_set = true;
   }
+  LaunchScope scope(CAT_ATTN_BWD, 10.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
   attn_bwd_kernel<<<dim3(d.heads, d.B), 128, BwdSmem::DYN, stream>>>(tm, a);
   VLPK_CUDA(cudaGetLastError());
   return 0;

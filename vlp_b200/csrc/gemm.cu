@@ -394,6 +394,7 @@ static int launch_inst(const GemmTmaps& tm, const GemmArgs& args, int num_work, 
     attr_set = true;
   }
   const int grid = num_work < num_sms() ? num_work : num_sms();
+  LaunchScope scope(A_MN ? CAT_GEMM_WGRAD : (B_MN ? CAT_GEMM_DGRAD : CAT_GEMM_FWD), 2.0 * args.M * args.N * args.K, stream);
   kfn<<<grid, NUM_THREADS, L::DYN_BYTES, stream>>>(tm, args);
   VLPK_CUDA(cudaGetLastError());
   return 0;

@@ -1,8 +1,10 @@
 // vlp_b200 — host-side utilities (see host.cuh).
 #include "host.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace vlpk {
 
@@ -77,6 +79,81 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ------------------------------------------------------------------------------------------------
+struct ProfRec {
+  int cat;
+  double work;
+  cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+static std::atomic<long long> g_launches{0};
+
+void prof_enable(bool on) { g_prof_on = on; }
+long long launch_count() { return g_launches.load(); }
+
+void prof_reset() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_recs) {
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_recs.clear();
+}
+
+static cudaEvent_t get_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+LaunchScope::LaunchScope(int cat, double work, cudaStream_t s) : idx_(-1), s_(s) {
+  g_launches.fetch_add(1);
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.cat = cat;
+  r.work = work;
+  r.e0 = get_event();
+  r.e1 = get_event();
+  cudaEventRecord(r.e0, s);
+  idx_ = static_cast<int>(g_recs.size());
+  g_recs.push_back(r);
+}
+LaunchScope::~LaunchScope() {
+  if (idx_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_recs[idx_].e1, s_);
+}
+
+int prof_get(int cat, double* ms, double* work, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tms = 0, tw = 0;
+  long long n = 0;
+  for (auto& r : g_recs) {
+    if (r.cat != cat) continue;
+    VLPK_CUDA(cudaEventSynchronize(r.e1));
+    float f = 0.f;
+    VLPK_CUDA(cudaEventElapsedTime(&f, r.e0, r.e1));
+    tms += f;
+    tw += r.work;
+    ++n;
+  }
+  *ms = tms;
+  *work = tw;
+  *launches = n;
+  return 0;
 }
 
 }  // namespace vlpk

@@ -55,4 +55,21 @@ inline int make_tmap_2d(CUtensorMap* out, TmapDtype dt, const void* base, uint64
 
 int num_sms();
 
+// ---- launch accounting + optional per-kernel-family timing (CUDA events on the launch stream) ----
+enum KernelCat { CAT_GEMM_FWD = 0, CAT_GEMM_DGRAD, CAT_GEMM_WGRAD, CAT_ATTN_FWD, CAT_ATTN_BWD, CAT_LN_FWD, CAT_LN_BWD, CAT_EMBED,
+                 CAT_MISC, CAT_COUNT };
+void prof_enable(bool on);
+void prof_reset();
+// Sums over all launches recorded since the last reset (synchronises the recorded events).
+int prof_get(int cat, double* ms, double* work, long long* launches);
+long long launch_count();
+// RAII: counts one kernel launch; when profiling is enabled brackets it with events.  `work` = algorithmic FLOPs
+// (tensor-bound kernels) or algorithmic HBM bytes (bandwidth-bound kernels) of this launch.
+struct LaunchScope {
+  LaunchScope(int cat, double work, cudaStream_t s);
+  ~LaunchScope();
+  int idx_;
+  cudaStream_t s_;
+};
+
 }  // namespace vlpk

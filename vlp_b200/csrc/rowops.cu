@@ -212,6 +212,7 @@ int launch_ln_res_drop_fwd(const LnArgs& a, cudaStream_t s) {
   VLPK_TRY(check_ln(a));
   const int wpb = 8;
   const long long grid = (a.M + wpb - 1) / wpb;
+  LaunchScope scope(CAT_LN_FWD, 2.0 * a.M * a.H * (a.res ? 3 : 2) + 8.0 * a.M, s);
   ln_res_drop_fwd_kernel<<<static_cast<unsigned>(grid), wpb * 32, 0, s>>>(a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
@@ -229,6 +230,7 @@ int launch_ln_res_drop_bwd(const LnArgs& a, cudaStream_t s) {
     VLPK_CUDA(cudaFuncSetAttribute(ln_res_drop_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
     attr_set = true;
   }
+  LaunchScope scope(CAT_LN_BWD, 2.0 * a.M * a.H * ((a.res ? 3 : 2) + (a.dz ? 1 : 0) + (a.dt ? 1 : 0)) + 8.0 * a.M, s);
   ln_res_drop_bwd_kernel<<<static_cast<unsigned>(grid), wpb * 32, smem, s>>>(a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
@@ -386,6 +388,7 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t s) {
   VLPK_TRY(check_embed(a));
   const int wpb = 8;
   const long long M = static_cast<long long>(a.B) * a.L;
+  LaunchScope scope(CAT_EMBED, 2.0 * M * a.H * 4, s);
   embed_fwd_kernel<<<static_cast<unsigned>((M + wpb - 1) / wpb), wpb * 32, 0, s>>>(a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
@@ -405,6 +408,7 @@ int launch_embed_bwd(const EmbedArgs& a, cudaStream_t s) {
     VLPK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
     attr_set = true;
   }
+  LaunchScope scope(CAT_EMBED, 2.0 * M * a.H * 5, s);
   embed_bwd_kernel<<<static_cast<unsigned>(grid), wpb * 32, smem, s>>>(a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
@@ -441,6 +445,7 @@ int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int
   VLPK_CHECK_ARG(B > 0 && rows > 0 && kv > 0 && kv <= 128, "mask_pack: kv=%d must be in [1,128]", kv);
   const long long n = static_cast<long long>(B) * rows;
   const unsigned grid = static_cast<unsigned>((n + 127) / 128);
+  LaunchScope scope(CAT_MISC, 0.0, s);
   switch (dtype) {
     case VLPK_DT_F32: mask_pack_kernel<float><<<grid, 128, 0, s>>>(static_cast<const float*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
     case VLPK_DT_BF16: mask_pack_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
@@ -475,6 +480,7 @@ int launch_colsum(const void* x, long long ld, long long M, int N, float* out, c
   VLPK_CHECK_ARG(N % 8 == 0 && ld % 8 == 0, "colsum: N=%d ld=%lld must be multiples of 8", N, ld);
   const int rows_per_blk = 32;
   dim3 grid((N / 8 + 255) / 256, static_cast<unsigned>((M + rows_per_blk - 1) / rows_per_blk));
+  LaunchScope scope(CAT_MISC, 2.0 * M * N, s);
   colsum_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, M, N, rows_per_blk, out);
   VLPK_CUDA(cudaGetLastError());
   return 0;
@@ -501,6 +507,7 @@ int launch_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t s) {
   VLPK_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
                  "f32_to_bf16: pointers must be 16-byte aligned");
   const long long nthreads = (n + 7) / 8;
+  LaunchScope scope(CAT_MISC, 6.0 * n, s);
   f32_to_bf16_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(y), n);
   VLPK_CUDA(cudaGetLastError());
   return 0;

@@ -1,0 +1,337 @@
+"""torch.autograd glue between the nn.Module surface (vlp_modules.py) and the C ABI (libvlpk.so).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd tape.  Every forward/backward
+body is one (or a few) calls into the hand-written CUDA library — there is no PyTorch implementation of
+these ops anywhere in the package, so a missing library is a hard error.
+"""
+import ctypes as C
+import itertools
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+
+# ------------------------------------------------------------------------------------------------
+# dropout seeding
+# ------------------------------------------------------------------------------------------------
+_seed_counter = itertools.count(1)
+_seed_dev = None  # optional int64 CUDA tensor: added to the host seed on device (CUDA-graph replays)
+
+
+def set_device_seed_tensor(t):
+    """Register a 1-element int64 CUDA tensor whose value is added to every dropout seed at kernel run time.
+    Increment it between CUDA-graph replays to get fresh masks from a frozen launch sequence."""
+    global _seed_dev
+    _seed_dev = t
+
+
+def next_seed():
+    return (torch.initial_seed() * 1000003 + next(_seed_counter) * 7919) & 0x7FFFFFFFFFFFFFFF
+
+
+def _drop(p, seed):
+    if p <= 0.0 or seed is None:
+        return None
+    return L.VlpkDropout(float(p), int(seed), None if _seed_dev is None else _seed_dev.data_ptr())
+
+
+def _bf16c(t):
+    """bf16 + contiguous view/copy of a tensor (parameters of a bf16 model pass through untouched)."""
+    if t is None:
+        return None
+    if t.dtype != BF16:
+        t = t.to(BF16)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"vlp_b200: {what} must live on a CUDA device (no CPU path exists)")
+
+
+# ------------------------------------------------------------------------------------------------
+# attention mask -> bitmask
+# ------------------------------------------------------------------------------------------------
+def pack_mask(mask, mode="additive"):
+    """[B,1,R,KV] / [B,R,KV] additive (0/-10000) or 0/1 mask -> int32 [B,R,4] 'attend' bitmask (R may be 1)."""
+    _require_cuda(mask, "attention mask")
+    if mask.dim() == 4:
+        mask = mask[:, 0]
+    if mask.dim() == 2:
+        mask = mask[:, None, :]
+    mask = mask.contiguous()
+    B, R, KV = mask.shape
+    dt = {torch.float32: 1, torch.bfloat16: 0, torch.int64: 2}.get(mask.dtype)
+    if dt is None:
+        mask = mask.float()
+        dt = 1
+    out = torch.empty(B, R, 4, device=mask.device, dtype=torch.int32)
+    L.call("vlpk_mask_pack", mask.data_ptr(), dt, 0 if mode == "additive" else 1, B, R, KV, R * KV, KV, out.data_ptr(), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BertLayer stack
+# ------------------------------------------------------------------------------------------------
+PARAMS_PER_LAYER = 16  # order == _lib.WEIGHT_FIELDS
+
+
+def _layer_sizes(H, I):
+    # fp32 gradient arena layout of one layer, order == _lib.GRAD_FIELDS
+    return [3 * H * H, 3 * H, H * H, H, H, H, I * H, I, H * I, H, H, H]
+
+
+def _grad_views(arena, H, I):
+    """Views of one layer's fp32 (or converted) arena in the order of WEIGHT_FIELDS."""
+    sizes = _layer_sizes(H, I)
+    offs = [0]
+    for s in sizes:
+        offs.append(offs[-1] + s)
+    seg = {n: arena[offs[i]:offs[i + 1]] for i, n in enumerate(L.GRAD_FIELDS)}
+    wqkv, bqkv = seg["wqkv"].view(3, H, H), seg["bqkv"].view(3, H)
+    return [wqkv[0], wqkv[1], wqkv[2], bqkv[0], bqkv[1], bqkv[2], seg["wo"].view(H, H), seg["bo"], seg["ln1_g"], seg["ln1_b"],
+            seg["w1"].view(I, H), seg["b1"], seg["w2"].view(H, I), seg["b2"], seg["ln2_g"], seg["ln2_b"]]
+
+
+class _Acts:
+    """Per-layer activation buffers (one bf16 + one fp32 allocation for the whole stack)."""
+
+    def __init__(self, n_layers, B, Lq, H, heads, I, device, Lkv=None):
+        M = B * Lq
+        self.bf_sizes = [("qkv", M * 3 * H), ("ctx", M * H), ("t1", M * H), ("y1", M * H), ("u", M * I), ("hmid", M * I), ("t2", M * H),
+                         ("y", M * H)]
+        if Lkv is not None:
+            self.bf_sizes.append(("kv", B * Lkv * 2 * H))
+        self.f_sizes = [("lse", B * heads * Lq), ("stats1", 2 * M), ("stats2", 2 * M)]
+        per_bf = sum(s for _, s in self.bf_sizes)
+        per_f = sum(s for _, s in self.f_sizes)
+        self.bf = torch.empty(n_layers, per_bf, device=device, dtype=BF16)
+        self.f32 = torch.empty(n_layers, per_f, device=device, dtype=torch.float32)
+        self.structs = (L.VlpkLayerActs * n_layers)()
+        self.y = []
+        for i in range(n_layers):
+            st = self.structs[i]
+            off = 0
+            base = self.bf[i]
+            for name, sz in self.bf_sizes:
+                setattr(st, name, base[off:off + sz].data_ptr())
+                if name == "y":
+                    self.y.append(base[off:off + sz].view(B, Lq, H))
+                off += sz
+            if Lkv is None:
+                st.kv = None
+            off = 0
+            basef = self.f32[i]
+            for name, sz in self.f_sizes:
+                setattr(st, name, basef[off:off + sz].data_ptr())
+                off += sz
+
+
+def _weight_structs(params, n_layers):
+    ws = (L.VlpkLayerWeights * n_layers)()
+    for i in range(n_layers):
+        for j, name in enumerate(L.WEIGHT_FIELDS):
+            setattr(ws[i], name, params[i * PARAMS_PER_LAYER + j].data_ptr())
+    return ws
+
+
+class EncoderStackFn(torch.autograd.Function):
+    """n_layers x BertLayer (modeling.py:367-402) in one C call each way.  Returns every layer's output."""
+
+    @staticmethod
+    def forward(ctx, hidden, mask_bits, cfg, *params):
+        n_layers, heads, I, p_attn, p_hidden, training = cfg
+        _require_cuda(hidden, "hidden_states")
+        x = _bf16c(hidden)
+        B, Lq, H = x.shape
+        pk = [_bf16c(p) for p in params]
+        acts = _Acts(n_layers, B, Lq, H, heads, I, x.device)
+        shape = L.VlpkShape(B, Lq, Lq, H, heads, I)
+        ws = _weight_structs(pk, n_layers)
+        seed = next_seed() if (training and (p_attn > 0 or p_hidden > 0)) else None
+        drop = _drop(max(p_attn, p_hidden), seed)
+        L.call("vlpk_encoder_fwd", C.byref(shape), n_layers, ws, x.data_ptr(), mask_bits.data_ptr(), mask_bits.shape[1], acts.structs,
+               float(p_attn if training else 0.0), float(p_hidden if training else 0.0), drop, L.stream())
+        ctx.cfg = cfg
+        ctx.seed = seed
+        ctx.acts = acts
+        ctx.x = x
+        ctx.mask_bits = mask_bits
+        ctx.pk = pk
+        ctx.param_dtypes = [p.dtype for p in params]
+        ctx.mark_non_differentiable(mask_bits)
+        return tuple(acts.y)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        n_layers, heads, I, p_attn, p_hidden, training = ctx.cfg
+        x, acts = ctx.x, ctx.acts
+        B, Lq, H = x.shape
+        M = B * Lq
+        dev = x.device
+        if dys[-1] is None:
+            dys = list(dys)
+            dys[-1] = torch.zeros_like(x)
+        dyc = [None if d is None else _bf16c(d) for d in dys]
+        dy_ptrs = (C.c_void_p * n_layers)(*[None if d is None else d.data_ptr() for d in dyc])
+        per_layer = sum(_layer_sizes(H, I))
+        arena = torch.zeros(n_layers, per_layer, device=dev, dtype=torch.float32)
+        gs = (L.VlpkLayerGrads * n_layers)()
+        sizes = _layer_sizes(H, I)
+        for i in range(n_layers):
+            off = 0
+            for name, sz in zip(L.GRAD_FIELDS, sizes):
+                setattr(gs[i], name, arena[i, off:off + sz].data_ptr())
+                off += sz
+        scr_sizes = {"dz2": M * H, "dt2": M * H, "du": M * I, "dy1": M * H, "dz1": M * H, "dt1": M * H, "dctx": M * H, "dqkv": 3 * M * H,
+                     "dx": M * H}
+        scratch = torch.empty(sum(scr_sizes.values()), device=dev, dtype=BF16)
+        ws_s = L.VlpkBwdScratch()
+        off = 0
+        for name in L.SCRATCH_FIELDS:
+            setattr(ws_s, name, scratch[off:off + scr_sizes[name]].data_ptr())
+            off += scr_sizes[name]
+        dx0 = torch.empty_like(x)
+        shape = L.VlpkShape(B, Lq, Lq, H, heads, I)
+        ws = _weight_structs(ctx.pk, n_layers)
+        drop = _drop(max(p_attn, p_hidden), ctx.seed)
+        L.call("vlpk_encoder_bwd", C.byref(shape), n_layers, ws, x.data_ptr(), ctx.mask_bits.data_ptr(), ctx.mask_bits.shape[1], acts.structs,
+               dy_ptrs, dx0.data_ptr(), gs, C.byref(ws_s), float(p_attn if training else 0.0), float(p_hidden if training else 0.0), drop,
+               L.stream())
+        # gradient arena -> parameter dtype (one conversion kernel for the whole stack)
+        if all(dt == BF16 for dt in ctx.param_dtypes):
+            garena = torch.empty(n_layers, per_layer, device=dev, dtype=BF16)
+            L.call("vlpk_f32_to_bf16", arena.data_ptr(), garena.data_ptr(), arena.numel(), L.stream())
+        else:
+            garena = arena
+        grads = []
+        for i in range(n_layers):
+            for v, dt in zip(_grad_views(garena[i], H, I), ctx.param_dtypes[i * PARAMS_PER_LAYER:(i + 1) * PARAMS_PER_LAYER]):
+                grads.append(v if v.dtype == dt else v.to(dt))
+        ctx.acts = None
+        return (dx0, None, None) + tuple(grads)
+
+
+def layer_incremental_fwd(hidden, history, mask_bits, heads, I, params):
+    """BertLayer.forward with history_states (modeling.py:273-277, 389-390): inference only, q rows = hidden,
+    kv rows = cat(history, hidden)."""
+    x = _bf16c(hidden)
+    xkv = _bf16c(torch.cat((history.to(x.dtype), x), dim=1))
+    B, Lq, H = x.shape
+    Lkv = xkv.shape[1]
+    pk = [_bf16c(p) for p in params]
+    acts = _Acts(1, B, Lq, H, heads, I, x.device, Lkv=Lkv)
+    shape = L.VlpkShape(B, Lq, Lkv, H, heads, I)
+    ws = _weight_structs(pk, 1)
+    L.call("vlpk_layer_fwd", C.byref(shape), ws, x.data_ptr(), xkv.data_ptr(), mask_bits.data_ptr(), mask_bits.shape[1], acts.structs, 0.0, 0.0,
+           None, 0, L.stream())
+    return acts.y[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear (+ReLU +dropout): region projections
+# ------------------------------------------------------------------------------------------------
+class LinearActFn(torch.autograd.Function):
+    """y = dropout(relu(x W^T + b)) (modeling.py:1003-1018).  K is zero-padded to a multiple of 8 (TMA strides)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, p, training, site):
+        _require_cuda(x, "linear input")
+        N, K = w.shape
+        Kp = (K + 7) // 8 * 8
+        x2 = _bf16c(x.reshape(-1, K))
+        wc = _bf16c(w)
+        if Kp != K:
+            x2 = torch.nn.functional.pad(x2, (0, Kp - K))
+            wc = torch.nn.functional.pad(wc, (0, Kp - K))
+        bc = _bf16c(b)
+        M = x2.shape[0]
+        y = torch.empty(M, N, device=x.device, dtype=BF16)
+        seed = next_seed() if (training and p > 0 and act == 1) else None
+        drop = _drop(p, seed)
+        L.call("vlpk_linear_fwd", M, N, Kp, x2.data_ptr(), Kp, wc.data_ptr(), Kp, L.ptr(bc), y.data_ptr(), N, act, drop, site, L.stream())
+        ctx.save_for_backward(x2, wc, y)
+        ctx.meta = (act, p if seed is not None else 0.0, K, Kp, x.shape, w.dtype, None if b is None else b.dtype, x.dtype)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wc, y = ctx.saved_tensors
+        act, p, K, Kp, xshape, wdt, bdt, xdt = ctx.meta
+        M, N = y.shape
+        dyc = _bf16c(dy.reshape(M, N))
+        need_dx = ctx.needs_input_grad[0]
+        dpre = torch.empty(M, N, device=dyc.device, dtype=BF16) if act == 1 else None
+        dx = torch.empty(M, Kp, device=dyc.device, dtype=BF16) if need_dx else None
+        dw = torch.zeros(N, Kp, device=dyc.device, dtype=torch.float32)
+        db = torch.zeros(N, device=dyc.device, dtype=torch.float32) if bdt is not None else None
+        L.call("vlpk_linear_bwd", M, N, Kp, x2.data_ptr(), Kp, wc.data_ptr(), Kp, y.data_ptr(), N, dyc.data_ptr(), N, L.ptr(dpre), L.ptr(dx), Kp,
+               dw.data_ptr(), Kp, L.ptr(db), act, float(p), L.stream())
+        gx = dx[:, :K].reshape(xshape).to(xdt) if need_dx else None
+        return gx, dw[:, :K].to(wdt), (db.to(bdt) if db is not None else None), None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# Embeddings
+# ------------------------------------------------------------------------------------------------
+class EmbedFn(torch.autograd.Function):
+    """BertEmbeddings.forward (modeling.py:217-241)."""
+
+    @staticmethod
+    def forward(ctx, vis, vpe, word_w, pos_w, type_w, ln_g, ln_b, ids, tt, pos, vis_input, R, p, training):
+        _require_cuda(ids, "input_ids")
+        B, Lq = ids.shape
+        H = word_w.shape[1]
+        visc, vpec = (_bf16c(vis), _bf16c(vpe)) if vis_input else (None, None)
+        tabs = [_bf16c(t) for t in (word_w, pos_w, type_w, ln_g, ln_b)]
+        ids = ids.contiguous()
+        tt = None if tt is None else tt.contiguous()
+        pos = None if pos is None else pos.contiguous()
+        y = torch.empty(B, Lq, H, device=ids.device, dtype=BF16)
+        stats = torch.empty(B * Lq, 2, device=ids.device, dtype=torch.float32)
+        seed = next_seed() if (training and p > 0) else None
+        drop = _drop(p, seed)
+        L.call("vlpk_embed_fwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), tabs[0].data_ptr(), tabs[1].data_ptr(),
+               tabs[2].data_ptr(), L.ptr(visc), L.ptr(vpec), tabs[3].data_ptr(), tabs[4].data_ptr(), y.data_ptr(), stats.data_ptr(), drop, 1 << 20,
+               L.stream())
+        ctx.saved = (visc, vpec, tabs, ids, tt, pos, stats)
+        ctx.meta = (vis_input, R, p if seed is not None else 0.0, seed, [t.dtype for t in (vis, vpe, word_w, pos_w, type_w, ln_g, ln_b)] if vis_input
+                    else [None, None] + [t.dtype for t in (word_w, pos_w, type_w, ln_g, ln_b)])
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        visc, vpec, tabs, ids, tt, pos, stats = ctx.saved
+        vis_input, R, p, seed, dts = ctx.meta
+        B, Lq = ids.shape
+        H = tabs[0].shape[1]
+        dev = ids.device
+        dyc = _bf16c(dy)
+        dz = torch.empty(B, Lq, H, device=dev, dtype=BF16)
+        dg = torch.zeros(H, device=dev, dtype=torch.float32)
+        db = torch.zeros(H, device=dev, dtype=torch.float32)
+        drop = _drop(p, seed)
+        L.call("vlpk_embed_bwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), tabs[0].data_ptr(), tabs[1].data_ptr(),
+               tabs[2].data_ptr(), L.ptr(visc), L.ptr(vpec), tabs[3].data_ptr(), stats.data_ptr(), dyc.data_ptr(), dz.data_ptr(), dg.data_ptr(),
+               db.data_ptr(), drop, 1 << 20, L.stream())
+        # scatter of the pre-LN gradient: region rows go to the projections, the other rows to the tables
+        if vis_input:
+            d_vis = dz[:, 1:R + 1]
+            keep = torch.cat((torch.zeros(1, dtype=torch.long, device=dev), torch.arange(R + 1, Lq, device=dev)))
+            dz_tab = dz[:, keep].reshape(-1, H).float()
+            ids_tab = ids[:, keep].reshape(-1)
+            pos_tab = (pos[:, keep] if pos is not None else keep.unsqueeze(0).expand(B, -1)).reshape(-1)
+        else:
+            d_vis = None
+            dz_tab = dz.reshape(-1, H).float()
+            ids_tab = ids.reshape(-1)
+            pos_tab = (pos if pos is not None else torch.arange(Lq, device=dev).unsqueeze(0).expand(B, -1)).reshape(-1)
+        d_word = torch.zeros(tabs[0].shape, device=dev, dtype=torch.float32).index_add_(0, ids_tab, dz_tab)
+        d_pos = torch.zeros(tabs[1].shape, device=dev, dtype=torch.float32).index_add_(0, pos_tab, dz_tab)
+        tt_all = (tt if tt is not None else torch.zeros_like(ids)).reshape(-1)
+        d_type = torch.zeros(tabs[2].shape, device=dev, dtype=torch.float32).index_add_(0, tt_all, dz.reshape(-1, H).float())
+        out = [None if d_vis is None else d_vis.to(dts[0]), None if d_vis is None else d_vis.to(dts[1]), d_word.to(dts[2]), d_pos.to(dts[3]),
+               d_type.to(dts[4]), dg.to(dts[5]), db.to(dts[6])]
+        return tuple(out) + (None,) * 7
