@@ -77,7 +77,7 @@ typedef struct VlpkLayerActs {
   void* ctx;     /* [B*Lq, H]   attention context */
   void* t1;      /* [B*Lq, H]   attention.output.dense result */
   void* y1;      /* [B*Lq, H]   BertAttention output (after LayerNorm) */
-  void* u;       /* [B*Lq, I]   pre-GELU */
+  void* u;       /* [B*Lq, I]   gelu'(pre-activation): all that backward needs of it */
   void* hmid;    /* [B*Lq, I]   GELU output */
   void* t2;      /* [B*Lq, H]   output.dense result */
   void* y;       /* [B*Lq, H]   layer output */
@@ -102,8 +102,8 @@ typedef struct VlpkBwdScratch {
 
 int vlpk_version(void);
 const char* vlpk_last_error(void);
-/* bring-up only: override the MN-major UMMA descriptor geometry used by vlpk_gemm (defaults 8192,1024,2048). */
-void vlpk_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep);
+/* bring-up / A-B testing only: force the GEMM CTA-group size (0 = cost model, 1 = single CTA tiles, 2 = CTA pairs). */
+void vlpk_debug_set_cta_group(int cg);
 
 /* get_extended_attention_mask (modeling.py:807-833) -> per-row 128-bit "attend" bitmask.
  * mask: [B, rows, kv] with element strides (stride_b, stride_r, 1); rows may be 1 (2-D mask). out: [B, rows, 4] u32. */

@@ -77,6 +77,14 @@ def test_model_matches_reference_golden(name, golden_dir):
         if fp is None:
             continue
         assert p.grad is not None, k
+        if k.endswith("attention.self.key.bias"):
+            # softmax is invariant to a per-query constant, so d(loss)/d(key.bias) is exactly 0 in exact arithmetic: the
+            # reference stores fp32 round-off (~1e-9), here it is bf16 round-off.  Compare against the scale of the
+            # sibling query.bias gradient instead of a relative error on noise.
+            sib = gold["grads"][k.replace("key.bias", "query.bias")]["full"].norm().item()
+            assert fp["full"].norm().item() < 1e-3 * sib
+            assert p.grad.float().norm().item() < 5e-2 * sib + 1e-6, (k, p.grad.float().norm().item(), sib)
+            continue
         if "full" in fp:
             ref = fp["full"]
             if ref.norm() == 0:

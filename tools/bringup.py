@@ -41,6 +41,10 @@ def gemm(M, N, K, A, B, a_mn=0, b_mn=0, bias=None, epi=0, aux=None, splits=1, bn
 
 
 def case_gemm_kk():
+    return _both_cta_groups(_gemm_kk)
+
+
+def _gemm_kk():
     ok = True
     torch.manual_seed(0)
     for (M, N, K, bn) in [(128, 128, 64, 128), (300, 256, 192, 128), (300, 256, 192, 256), (1000, 768, 768, 0), (7872, 2304, 768, 0)]:
@@ -59,6 +63,10 @@ def case_gemm_kk():
 
 
 def case_gemm_epi():
+    return _both_cta_groups(_gemm_epi)
+
+
+def _gemm_epi():
     ok = True
     torch.manual_seed(1)
     M, N, K = 520, 512, 256
@@ -69,27 +77,25 @@ def case_gemm_epi():
     D1 = torch.zeros(M, N, device=DEV, dtype=BF)
     U = gemm(M, N, K, A, B, bias=bias, epi=1, D1=D1)
     torch.cuda.synchronize()
-    ok &= report("gelu: u", U, u_ref)
-    ok &= report("gelu: h", D1, torch.nn.functional.gelu(u_ref))
+    gp_ref = 0.5 * (1 + torch.erf(u_ref / math.sqrt(2))) + u_ref * torch.exp(-0.5 * u_ref * u_ref) / math.sqrt(2 * math.pi)
+    ok &= report("gelu: gelu'(u)", U, gp_ref)
+    ok &= report("gelu: gelu(u)", D1, torch.nn.functional.gelu(u_ref))
     R = gemm(M, N, K, A, B, bias=bias, epi=2)
     ok &= report("relu", R, torch.relu(u_ref))
     return ok
 
 
-def _sweep_mn(fn):
-    """Try the designed MN-major descriptor geometry first, then alternatives (diagnostics only)."""
-    cands = [(8192, 1024, 2048), (1024, 8192, 2048), (8192, 1024, 256), (1024, 8192, 256), (16, 1024, 2048), (128, 1024, 2048)]
-    for i, (lbo, sbo, ks) in enumerate(cands):
-        L.lib().vlpk_debug_set_mn_desc(lbo, sbo, ks)
-        print(f" MN desc lbo={lbo} sbo={sbo} kstep={ks}")
+def _both_cta_groups(fn):
+    """Run a GEMM case with single-CTA tiles, with cta_group::2 CTA pairs, and with the cost model's own choice."""
+    ok = True
+    for cg in (1, 2, 0):
+        L.lib().vlpk_debug_set_cta_group(cg)
+        print(f" cta_group {'auto' if cg == 0 else cg}")
         try:
-            good = fn()
+            ok &= fn()
         finally:
-            L.lib().vlpk_debug_set_mn_desc(8192, 1024, 2048)
-        if good:
-            print(f" -> geometry {(lbo, sbo, ks)} PASSES" + ("" if i == 0 else "  (NOT the designed one!)"))
-            return i == 0
-    return False
+            L.lib().vlpk_debug_set_cta_group(0)
+    return ok
 
 
 def case_gemm_dgrad():
@@ -108,12 +114,10 @@ def case_gemm_dgrad():
         aux = torch.randn(M, N, device=DEV).to(BF)
         ref = A.float() @ Bs.float()
         ok &= report("dgrad +aux", gemm(M, N, K, A, Bs, b_mn=1, epi=3, aux=aux), ref + aux.float())
-        x = aux.float()
-        gp = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
-        ok &= report("dgrad *gelu'", gemm(M, N, K, A, Bs, b_mn=1, epi=4, aux=aux), ref * gp)
+        ok &= report("dgrad *aux", gemm(M, N, K, A, Bs, b_mn=1, epi=4, aux=aux), ref * aux.float())
         return ok
 
-    return _sweep_mn(run)
+    return _both_cta_groups(run)
 
 
 def case_gemm_wgrad():
@@ -130,7 +134,7 @@ def case_gemm_wgrad():
             ok &= report(f"wgrad T{T} N{Nf} K{Kf} s{splits} bn{bn}", D, ref)
         return ok
 
-    return _sweep_mn(run)
+    return _both_cta_groups(run)
 
 
 def _mask_bits(mask01):
@@ -257,6 +261,15 @@ def case_rowops():
 
 
 def case_perf():
+    for cg in (1, 2, 0):
+        L.lib().vlpk_debug_set_cta_group(cg)
+        print(f" cta_group {'auto' if cg == 0 else cg}")
+        _perf(cg == 0)
+    L.lib().vlpk_debug_set_cta_group(0)
+    return True
+
+
+def _perf(extras):
     """Quick device-time numbers for the hot shapes (CUDA events, L2-sized rotation not applied: indicative only)."""
     torch.manual_seed(6)
     M = 7872
@@ -274,16 +287,19 @@ def case_perf():
         ms = e0.elapsed_time(e1) / iters
         print(f"  {name:36s} {ms * 1e3:9.1f} us  {flops / ms / 1e9:8.1f} TFLOP/s")
 
-    for (N, K, bn) in [(2304, 768, 0), (768, 768, 0), (3072, 768, 0), (768, 3072, 0), (768, 768, 128), (768, 768, 256), (2304, 768, 128), (2304, 768, 256)]:
+    for (N, K, bn) in [(2304, 768, 0), (768, 768, 0), (3072, 768, 0), (768, 3072, 0), (768, 768, 128), (768, 768, 256), (3072, 768, 128), (3072, 768, 256)]:
         A = torch.randn(M, K, device=DEV).to(BF); B = torch.randn(N, K, device=DEV).to(BF); D = torch.zeros(M, N, device=DEV, dtype=BF)
         timeit(lambda: gemm(M, N, K, A, B, bn=bn, D0=D), 2.0 * M * N * K, f"fwd  {M}x{N}x{K} bn{bn}")
-        timeit(lambda: torch.matmul(A, B.t(), out=D), 2.0 * M * N * K, f"cublas {M}x{N}x{K}")
+        if extras:
+            timeit(lambda: torch.matmul(A, B.t(), out=D), 2.0 * M * N * K, f"cublas {M}x{N}x{K}")
     for (N, K) in [(3072, 768), (768, 3072)]:
         A = torch.randn(M, K, device=DEV).to(BF); Bs = torch.randn(K, N, device=DEV).to(BF); D = torch.zeros(M, N, device=DEV, dtype=BF)
         timeit(lambda: gemm(M, N, K, A, Bs, b_mn=1, D0=D), 2.0 * M * N * K, f"dgrad {M}x{N}x{K}")
-    for (Nf, Kf, s) in [(768, 768, 8), (768, 3072, 4), (3072, 768, 4), (2304, 768, 5)]:
+    for (Nf, Kf, s) in [(768, 768, 0), (768, 3072, 0), (3072, 768, 0), (2304, 768, 0)]:
         dY = torch.randn(M, Nf, device=DEV).to(BF); X = torch.randn(M, Kf, device=DEV).to(BF); D = torch.zeros(Nf, Kf, device=DEV)
         timeit(lambda: gemm(Nf, Kf, M, dY, X, a_mn=1, b_mn=1, epi=6, splits=s, out_f32=True, D0=D), 2.0 * M * Nf * Kf, f"wgrad {Nf}x{Kf}x{M} s{s}")
+    if not extras:
+        return True
     B, heads, Lq, H = 64, 12, 123, 768
     qkv = torch.randn(B, Lq, 3 * H, device=DEV).to(BF)
     bits = torch.full((B, Lq, 4), -1, device=DEV, dtype=torch.int32)

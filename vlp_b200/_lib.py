@@ -51,7 +51,7 @@ _P = c_void_p
 _SIGS = {
     "vlpk_version": (c_int, []),
     "vlpk_last_error": (C.c_char_p, []),
-    "vlpk_debug_set_mn_desc": (None, [C.c_uint32, C.c_uint32, C.c_uint32]),
+    "vlpk_debug_set_cta_group": (None, [c_int]),
     "vlpk_mask_pack": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, c_i64, c_i64, _P, _P]),
     "vlpk_linear_fwd": (c_int, [c_int, c_int, c_int, _P, c_i64, _P, c_i64, _P, _P, c_i64, c_int, C.POINTER(VlpkDropout), c_u64, _P]),
     "vlpk_linear_bwd": (c_int, [c_int, c_int, c_int, _P, c_i64, _P, c_i64, _P, c_i64, _P, c_i64, _P, _P, c_i64, _P, c_i64, _P,

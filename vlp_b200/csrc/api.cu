@@ -37,17 +37,6 @@ int check_shape(const VlpkShape* s) {
   return 0;
 }
 
-// Split-K factor for a weight-gradient GEMM: aim at ~2 waves of work items, at least 8 k-blocks each.
-int wgrad_splits(int Mg, int Ng, int Kg) {
-  const int tiles = ((Mg + 127) / 128) * ((Ng + 255) / 256);
-  const int total_kb = (Kg + 63) / 64;
-  int s = (2 * num_sms() + tiles - 1) / tiles;
-  const int max_s = total_kb / 8 > 0 ? total_kb / 8 : 1;
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  return s;
-}
-
 // y[M,N] = x[M,K] w[N,K]^T + b   (single weight)
 int fwd_linear(int M, int N, int K, const void* x, int64_t ldx, const void* w, int64_t ldw, const void* b, void* y, int64_t ldy,
                int epi, void* y1, int64_t ldy1, const DropoutCfg& drop, cudaStream_t st) {
@@ -84,7 +73,7 @@ int wgrad_linear(int M, int N, int K, const void* dy, int64_t lddy, const void* 
   g.b_mn = true; g.B[0] = x; g.ldb = ldx; g.nseg = 1;
   g.D0 = dw; g.ldd0 = lddw;
   g.epi = EPI_REDUCE_F32;
-  g.splits = wgrad_splits(N, K, M);
+  g.splits = 0;  // chosen together with the tile shape by launch_gemm's cost model
   return launch_gemm(g, st);
 }
 
@@ -177,9 +166,9 @@ int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
   l2.drop = mk_drop(drop, p_hidden, site_of(layer_id, SITE_HID2));
   VLPK_TRY(launch_ln_res_drop_bwd(l2, st));
   const void* dt2 = hdrop ? ws->dt2 : ws->dz2;
-  // ---- output.dense: dW2 += dt2^T hmid ; dU = (dt2 W2) * gelu'(u)
+  // ---- output.dense: dW2 += dt2^T hmid ; dU = (dt2 W2) * gelu'(u)   [gelu'(u) was stored by the forward epilogue in acts.u]
   VLPK_TRY(wgrad_linear(M, H, I, dt2, H, a->hmid, I, g->w2, I, st));
-  VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_DGELU, a->u, I, st));
+  VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, st));
   // ---- intermediate.dense: db1, dW1 += dU^T y1 ; dy1 = dU W1 + dz2 (residual branch of LN2)
   VLPK_TRY(launch_colsum(ws->du, I, M, I, g->b1, st));
   VLPK_TRY(wgrad_linear(M, I, H, ws->du, I, a->y1, H, g->w1, H, st));
@@ -264,7 +253,7 @@ __global__ void relu_bwd_kernel(bf16* __restrict__ dpre, const bf16* __restrict_
 extern "C" {
 
 int vlpk_version(void) { return VLPK_VERSION; }
-void vlpk_debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep) { debug_set_mn_desc(lbo, sbo, kstep); }
+void vlpk_debug_set_cta_group(int cg) { debug_set_cta_group(cg); }
 const char* vlpk_last_error(void) { return get_error(); }
 
 int vlpk_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, int64_t stride_b, int64_t stride_r, uint32_t* out,

@@ -212,12 +212,24 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// erf-GELU exactly as the reference defines it (pytorch_pretrained_bert/modeling.py:62-67).
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+// erf-GELU of the reference (pytorch_pretrained_bert/modeling.py:62-67): gelu(x) = x * 0.5 * (1 + erf(x / sqrt 2)), and its
+// derivative gelu'(x) = Phi(x) + x * phi(x).  erf is evaluated with Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e.
+// below fp32 round-off of the surrounding arithmetic and 4 orders below bf16 resolution); it shares one exp(-x^2/2) with
+// the density term, so the pair costs one MUFU.EX2 + one MUFU.RCP + ~12 FMAs.  (This is the erf form, not the tanh
+// approximation the reference explicitly does not use.)
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& d) {
+  const float ax = fabsf(x);
+  const float e = __expf(-0.5f * x * x);
+  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, e, 1.0f);        // erf(|x|/sqrt2)
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  g = x * cdf;
+  d = fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -9,10 +9,10 @@ namespace vlpk {
 // (66 % of reference self-time is unfused elementwise glue).
 enum Epi : int {
   EPI_STORE = 0,       // D0 = acc (+ bias)
-  EPI_GELU = 1,        // D0 = u = acc + bias ; D1 = gelu_erf(u)          (modeling.py:340-343, 62-67)
+  EPI_GELU = 1,        // u = acc + bias ; D0 = gelu'(u) ; D1 = gelu(u)    (modeling.py:340-343, 62-67)
   EPI_RELU = 2,        // D0 = dropout(relu(acc + bias))                   (modeling.py:1003-1018)
   EPI_ADD = 3,         // D0 = acc + aux                                   (dgrad + residual-branch gradient)
-  EPI_DGELU = 4,       // D0 = acc * gelu_erf'(aux)                        (dgrad through BertIntermediate)
+  EPI_MUL = 4,         // D0 = acc * aux                                   (dgrad through GELU: aux = saved gelu'(u))
   EPI_DRELU = 5,       // D0 = acc * (aux > 0) * relu_scale                (dgrad through ReLU(+dropout))
   EPI_REDUCE_F32 = 6,  // D0(fp32) += acc   via TMA reduce-add (split-K weight gradients)
 };
@@ -41,12 +41,12 @@ struct GemmDesc {
   int epi = EPI_STORE;
   float relu_scale = 1.0f;  // EPI_DRELU: 1/(1-p) of the forward dropout
   DropoutCfg drop = {0.f, 1.f, 0u, 0ull, 0ull, nullptr};
-  int splits = 1;  // split-K (EPI_REDUCE_F32 only)
+  int splits = 1;  // split-K (EPI_REDUCE_F32 only); 0 = choose automatically
   int bn = 0;      // tile N (0 = auto)
 };
 
 // Returns 0 on success, <0 on argument error, >0 cudaError_t.  Message via vlpk::set_error.
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
-void debug_set_mn_desc(uint32_t lbo, uint32_t sbo, uint32_t kstep);
+void debug_set_cta_group(int cg);
 
 }  // namespace vlpk

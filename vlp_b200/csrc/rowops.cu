@@ -12,7 +12,8 @@
 
 namespace vlpk {
 
-static constexpr int MAXCH = 4;  // up to 4 x (32 lanes x 8 elems) = 1024 columns per row
+static constexpr int MAXCH = 4;  // up to 4 x (32 lanes x 8 elems) = 1024 columns per row; kernels are templated on
+                                 // NCH = ceil(H / 256) so that per-row state stays in registers without padding to the maximum
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -40,11 +41,12 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 }
 
 // mean / rstd of a row distributed as z[i][0..7] over the warp (two-pass, fp32)
-__device__ __forceinline__ void row_stats(const float (&z)[MAXCH][8], const bool (&ok)[MAXCH], int H, float eps,
+template <int NCH>
+__device__ __forceinline__ void row_stats(const float (&z)[NCH][8], const bool (&ok)[NCH], int H, float eps,
                                           float& mean, float& rstd) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i)
+  for (int i = 0; i < NCH; ++i)
     if (ok[i]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += z[i][j];
@@ -52,7 +54,7 @@ __device__ __forceinline__ void row_stats(const float (&z)[MAXCH][8], const bool
   mean = warp_sum(s) / H;
   float v = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i)
+  for (int i = 0; i < NCH; ++i)
     if (ok[i]) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -66,16 +68,17 @@ __device__ __forceinline__ void row_stats(const float (&z)[MAXCH][8], const bool
 // ------------------------------------------------------------------------------------------------
 // LN + residual + dropout
 // ------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(256) ln_res_drop_fwd_kernel(LnArgs a) {
   const uint64_t dseed = drop_seed(a.drop);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const long long rowi = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5);
   if (rowi >= a.M) return;
-  float z[MAXCH][8];
-  bool ok[MAXCH];
+  float z[NCH][8];
+  bool ok[NCH];
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int col = (lane + 32 * i) * 8;
     ok[i] = col < a.H;
     if (ok[i]) {
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(256) ln_res_drop_fwd_kernel(LnArgs a) {
   float mean, rstd;
   row_stats(z, ok, a.H, a.eps, mean, rstd);
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int col = (lane + 32 * i) * 8;
     if (ok[i]) {
       float g[8], be[8], y[8];
@@ -106,36 +109,58 @@ __global__ void __launch_bounds__(256) ln_res_drop_fwd_kernel(LnArgs a) {
   if (lane == 0 && a.stats != nullptr) a.stats[rowi] = make_float2(mean, rstd);
 }
 
-// Backward.  Persistent warps accumulate dgamma/dbeta(/dbias) over their rows in registers, then one
-// shared-memory reduction + one fp32 atomicAdd per column per block.
-__global__ void __launch_bounds__(256) ln_res_drop_bwd_kernel(LnArgs a) {
+// Backward.  One 16-warp block per SM; each warp walks rows (grid-stride) and keeps its dgamma / dbeta / dbias partial sums
+// in a private slice of shared memory (float4 read-modify-write, lane-interleaved so every access is conflict free) instead
+// of 72+ accumulator registers per thread: ~90 registers/thread -> 16 resident warps/SM with 9 independent 16-byte loads in
+// flight per lane, which is what an HBM-bound kernel needs.  One smem reduction + one fp32 atomicAdd per column per block.
+static constexpr int LNB_WARPS = 16;
+
+// index of (chunk i, lane l, element j) of a per-warp [NCH*256] accumulator: two float4 halves, lanes adjacent
+__device__ __forceinline__ int lnb_idx(int i, int half, int lane) { return ((i * 2 + half) * 32 + lane) * 4; }
+
+template <int NCH>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1) ln_res_drop_bwd_kernel(LnArgs a) {
   const uint64_t dseed = drop_seed(a.drop);
-  extern __shared__ float s_red[];  // [wpb][3][H]
+  extern __shared__ float s_ln[];       // [LNB_WARPS][3][NCH*256] accumulators, then gamma [NCH*256]
+  constexpr int W = NCH * 256;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int wpb = blockDim.x >> 5;
-  float ag[MAXCH][8], ab[MAXCH][8], at[MAXCH][8];
-  bool ok[MAXCH];
+  float* sg = s_ln + (wib * 3 + 0) * W;
+  float* sb = s_ln + (wib * 3 + 1) * W;
+  float* st = s_ln + (wib * 3 + 2) * W;
+  float* s_gamma = s_ln + LNB_WARPS * 3 * W;
+  bool ok[NCH];
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     ok[i] = (lane + 32 * i) * 8 < a.H;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = at[i][j] = 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(sg + lnb_idx(i, h, lane)) = z4;
+      *reinterpret_cast<float4*>(sb + lnb_idx(i, h, lane)) = z4;
+      *reinterpret_cast<float4*>(st + lnb_idx(i, h, lane)) = z4;
+    }
   }
-  float g[MAXCH][8];
+  if (wib == 0) {
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i)
-    if (ok[i]) load8(a.gamma + (lane + 32 * i) * 8, g[i]);
+    for (int i = 0; i < NCH; ++i) {
+      float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (ok[i]) load8(a.gamma + (lane + 32 * i) * 8, g);
+      *reinterpret_cast<float4*>(s_gamma + lnb_idx(i, 0, lane)) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(s_gamma + lnb_idx(i, 1, lane)) = make_float4(g[4], g[5], g[6], g[7]);
+    }
+  }
+  __syncthreads();
 
-  for (long long rowi = static_cast<long long>(blockIdx.x) * wpb + wib; rowi < a.M;
-       rowi += static_cast<long long>(gridDim.x) * wpb) {
-    const float2 st = a.stats[rowi];
-    const float mean = st.x, rstd = st.y;
-    float xh[MAXCH][8], gy[MAXCH][8];
-    uint32_t keepm[MAXCH];
+  for (long long rowi = static_cast<long long>(blockIdx.x) * LNB_WARPS + wib; rowi < a.M;
+       rowi += static_cast<long long>(gridDim.x) * LNB_WARPS) {
+    const float2 stt = a.stats[rowi];
+    const float mean = stt.x, rstd = stt.y;
+    float xh[NCH][8], gy[NCH][8];
+    uint32_t keepm[NCH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int col = (lane + 32 * i) * 8;
       keepm[i] = 0xFFu;
       if (ok[i]) {
@@ -144,21 +169,38 @@ __global__ void __launch_bounds__(256) ln_res_drop_bwd_kernel(LnArgs a) {
         if (a.res != nullptr) load8(a.res + rowi * a.H + col, r);
         load8(a.dy + rowi * a.H + col, dy);
         if (a.drop.p > 0.f) keepm[i] = dropout_keep8(dseed, a.drop.site, (rowi * a.H + col) >> 3, a.drop.thresh16);
+        float g[8];
+        {
+          const float4 g0 = *reinterpret_cast<const float4*>(s_gamma + lnb_idx(i, 0, lane));
+          const float4 g1 = *reinterpret_cast<const float4*>(s_gamma + lnb_idx(i, 1, lane));
+          g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+        }
+        float pg[8], pb[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float zz = (((keepm[i] >> j) & 1u) ? t[j] * a.drop.scale : 0.f) + r[j];
           xh[i][j] = (zz - mean) * rstd;
-          gy[i][j] = dy[j] * g[i][j];
+          gy[i][j] = dy[j] * g[j];
           s1 += gy[i][j];
           s2 += gy[i][j] * xh[i][j];
-          ag[i][j] += dy[j] * xh[i][j];
-          ab[i][j] += dy[j];
+          pg[j] = dy[j] * xh[i][j];
+          pb[j] = dy[j];
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4* pgs = reinterpret_cast<float4*>(sg + lnb_idx(i, h, lane));
+          float4* pbs = reinterpret_cast<float4*>(sb + lnb_idx(i, h, lane));
+          float4 vg = *pgs, vb = *pbs;
+          vg.x += pg[4 * h]; vg.y += pg[4 * h + 1]; vg.z += pg[4 * h + 2]; vg.w += pg[4 * h + 3];
+          vb.x += pb[4 * h]; vb.y += pb[4 * h + 1]; vb.z += pb[4 * h + 2]; vb.w += pb[4 * h + 3];
+          *pgs = vg;
+          *pbs = vb;
         }
       }
     }
     const float c1 = warp_sum(s1) / a.H, c2 = warp_sum(s2) / a.H;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int col = (lane + 32 * i) * 8;
       if (ok[i]) {
         float dz[8], dt[8];
@@ -166,41 +208,46 @@ __global__ void __launch_bounds__(256) ln_res_drop_bwd_kernel(LnArgs a) {
         for (int j = 0; j < 8; ++j) {
           dz[j] = rstd * (gy[i][j] - c1 - xh[i][j] * c2);
           dt[j] = ((keepm[i] >> j) & 1u) ? dz[j] * a.drop.scale : 0.f;
-          at[i][j] += dt[j];
         }
         if (a.dz != nullptr) store8(a.dz + rowi * a.H + col, dz);
         if (a.dt != nullptr) store8(a.dt + rowi * a.H + col, dt);
+        if (a.dbias != nullptr) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4* pts = reinterpret_cast<float4*>(st + lnb_idx(i, h, lane));
+            float4 vt = *pts;
+            vt.x += dt[4 * h]; vt.y += dt[4 * h + 1]; vt.z += dt[4 * h + 2]; vt.w += dt[4 * h + 3];
+            *pts = vt;
+          }
+        }
       }
     }
   }
-  // block reduction
-  float* sg = s_red + (wib * 3 + 0) * a.H;
-  float* sb = s_red + (wib * 3 + 1) * a.H;
-  float* stt = s_red + (wib * 3 + 2) * a.H;
-#pragma unroll
-  for (int i = 0; i < MAXCH; ++i)
-    if (ok[i]) {
-      const int col = (lane + 32 * i) * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sg[col + j] = ag[i][j];
-        sb[col + j] = ab[i][j];
-        stt[col + j] = at[i][j];
-      }
-    }
   __syncthreads();
+  // fold the 16 per-warp partials; column c lives at lnb_idx(c / 256, (c % 8) / 4, (c % 256) / 8) + c % 4
   for (int c = threadIdx.x; c < a.H; c += blockDim.x) {
+    const int idx = lnb_idx(c >> 8, (c & 7) >> 2, (c & 255) >> 3) + (c & 3);
     float vg = 0.f, vb = 0.f, vt = 0.f;
-    for (int w = 0; w < wpb; ++w) {
-      vg += s_red[(w * 3 + 0) * a.H + c];
-      vb += s_red[(w * 3 + 1) * a.H + c];
-      vt += s_red[(w * 3 + 2) * a.H + c];
+#pragma unroll 4
+    for (int w = 0; w < LNB_WARPS; ++w) {
+      vg += s_ln[(w * 3 + 0) * W + idx];
+      vb += s_ln[(w * 3 + 1) * W + idx];
+      vt += s_ln[(w * 3 + 2) * W + idx];
     }
     if (a.dgamma != nullptr) atomicAdd(a.dgamma + c, vg);
     if (a.dbeta != nullptr) atomicAdd(a.dbeta + c, vb);
     if (a.dbias != nullptr) atomicAdd(a.dbias + c, vt);
   }
 }
+
+#define VLPK_DISPATCH_NCH(H, ...)                  \
+  do {                                             \
+    const int _nch = ((H) + 255) / 256;            \
+    if (_nch == 1) { constexpr int NCH = 1; __VA_ARGS__; }      \
+    else if (_nch == 2) { constexpr int NCH = 2; __VA_ARGS__; } \
+    else if (_nch == 3) { constexpr int NCH = 3; __VA_ARGS__; } \
+    else { constexpr int NCH = 4; __VA_ARGS__; }   \
+  } while (0)
 
 static int check_ln(const LnArgs& a) {
   VLPK_CHECK_ARG(a.M > 0 && a.H > 0 && a.H % 8 == 0 && a.H <= MAXCH * 256, "layernorm: H=%d must be a multiple of 8 and <= %d",
@@ -213,25 +260,28 @@ int launch_ln_res_drop_fwd(const LnArgs& a, cudaStream_t s) {
   const int wpb = 8;
   const long long grid = (a.M + wpb - 1) / wpb;
   LaunchScope scope(CAT_LN_FWD, 2.0 * a.M * a.H * (a.res ? 3 : 2) + 8.0 * a.M, s);
-  ln_res_drop_fwd_kernel<<<static_cast<unsigned>(grid), wpb * 32, 0, s>>>(a);
+  VLPK_DISPATCH_NCH(a.H, ln_res_drop_fwd_kernel<NCH><<<static_cast<unsigned>(grid), wpb * 32, 0, s>>>(a));
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_ln_res_drop_bwd(const LnArgs& a, cudaStream_t s) {
   VLPK_TRY(check_ln(a));
-  const int wpb = 8;
-  long long grid = (a.M + wpb - 1) / wpb;
-  const long long cap = static_cast<long long>(num_sms()) * 4;
-  if (grid > cap) grid = cap;
-  const size_t smem = static_cast<size_t>(wpb) * 3 * a.H * sizeof(float);
+  VLPK_CHECK_ARG(a.dy != nullptr && a.stats != nullptr, "layernorm bwd: missing dy / stats");
+  const int nch = (a.H + 255) / 256;
+  long long grid = (a.M + LNB_WARPS - 1) / LNB_WARPS;
+  if (grid > num_sms()) grid = num_sms();
+  const size_t smem = static_cast<size_t>(LNB_WARPS * 3 + 1) * nch * 256 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    VLPK_CUDA(cudaFuncSetAttribute(ln_res_drop_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 3 * 1024 * 4));
+    VLPK_CUDA(cudaFuncSetAttribute(ln_res_drop_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LNB_WARPS * 3 + 1) * 1 * 1024));
+    VLPK_CUDA(cudaFuncSetAttribute(ln_res_drop_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LNB_WARPS * 3 + 1) * 2 * 1024));
+    VLPK_CUDA(cudaFuncSetAttribute(ln_res_drop_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LNB_WARPS * 3 + 1) * 3 * 1024));
+    VLPK_CUDA(cudaFuncSetAttribute(ln_res_drop_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (LNB_WARPS * 3 + 1) * 4 * 1024));
     attr_set = true;
   }
   LaunchScope scope(CAT_LN_BWD, 2.0 * a.M * a.H * ((a.res ? 3 : 2) + (a.dz ? 1 : 0) + (a.dt ? 1 : 0)) + 8.0 * a.M, s);
-  ln_res_drop_bwd_kernel<<<static_cast<unsigned>(grid), wpb * 32, smem, s>>>(a);
+  VLPK_DISPATCH_NCH(a.H, ln_res_drop_bwd_kernel<NCH><<<static_cast<unsigned>(grid), LNB_WARPS * 32, smem, s>>>(a));
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -239,8 +289,8 @@ int launch_ln_res_drop_bwd(const LnArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // Embeddings: gather + region splice + LN + dropout
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void embed_row_z(const EmbedArgs& a, long long rowi, int lane, float (&z)[MAXCH][8],
-                                            bool (&ok)[MAXCH]) {
+template <int NCH>
+__device__ __forceinline__ void embed_row_z(const EmbedArgs& a, long long rowi, int lane, float (&z)[NCH][8], bool (&ok)[NCH]) {
   const int b = static_cast<int>(rowi / a.L), l = static_cast<int>(rowi % a.L);
   const bool vis = a.vis_input && l >= 1 && l <= a.R;
   const long long wid = a.ids[rowi];
@@ -250,7 +300,7 @@ __device__ __forceinline__ void embed_row_z(const EmbedArgs& a, long long rowi, 
   const __nv_bfloat16* psrc = vis ? a.vpe + (static_cast<long long>(b) * a.R + (l - 1)) * a.H : a.posw + pid * a.H;
   const __nv_bfloat16* tsrc = a.typew + tid * a.H;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int col = (lane + 32 * i) * 8;
     ok[i] = col < a.H;
     if (ok[i]) {
@@ -264,6 +314,7 @@ __device__ __forceinline__ void embed_row_z(const EmbedArgs& a, long long rowi, 
   }
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a) {
   const uint64_t dseed = drop_seed(a.drop);
   const int lane = threadIdx.x & 31;
@@ -271,13 +322,13 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a) {
   const long long rowi = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5);
   const long long M = static_cast<long long>(a.B) * a.L;
   if (rowi >= M) return;
-  float z[MAXCH][8];
-  bool ok[MAXCH];
+  float z[NCH][8];
+  bool ok[NCH];
   embed_row_z(a, rowi, lane, z, ok);
   float mean, rstd;
   row_stats(z, ok, a.H, a.eps, mean, rstd);
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     const int col = (lane + 32 * i) * 8;
     if (ok[i]) {
       float g[8], be[8], y[8];
@@ -296,6 +347,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(EmbedArgs a) {
   if (lane == 0 && a.stats != nullptr) a.stats[rowi] = make_float2(mean, rstd);
 }
 
+template <int NCH>
 __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedArgs a) {
   const uint64_t dseed = drop_seed(a.drop);
   extern __shared__ float s_red[];  // [wpb][2][H]
@@ -303,10 +355,10 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedArgs a) {
   const int wib = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const long long M = static_cast<long long>(a.B) * a.L;
-  float ag[MAXCH][8], ab[MAXCH][8], g[MAXCH][8];
-  bool okc[MAXCH];
+  float ag[NCH][8], ab[NCH][8], g[NCH][8];
+  bool okc[NCH];
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < NCH; ++i) {
     okc[i] = (lane + 32 * i) * 8 < a.H;
     if (okc[i]) load8(a.gamma + (lane + 32 * i) * 8, g[i]);
 #pragma unroll
@@ -314,15 +366,15 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedArgs a) {
   }
   for (long long rowi = static_cast<long long>(blockIdx.x) * wpb + wib; rowi < M;
        rowi += static_cast<long long>(gridDim.x) * wpb) {
-    float z[MAXCH][8];
-    bool ok[MAXCH];
+    float z[NCH][8];
+    bool ok[NCH];
     embed_row_z(a, rowi, lane, z, ok);
     const float2 st = a.stats[rowi];
     const float mean = st.x, rstd = st.y;
-    float gy[MAXCH][8];
+    float gy[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int col = (lane + 32 * i) * 8;
       if (ok[i]) {
         float dy[8];
@@ -343,7 +395,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedArgs a) {
     }
     const float c1 = warp_sum(s1) / a.H, c2 = warp_sum(s2) / a.H;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < NCH; ++i) {
       const int col = (lane + 32 * i) * 8;
       if (ok[i]) {
         float dz[8];
@@ -356,7 +408,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(EmbedArgs a) {
   float* sg = s_red + (wib * 2 + 0) * a.H;
   float* sb = s_red + (wib * 2 + 1) * a.H;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i)
+  for (int i = 0; i < NCH; ++i)
     if (okc[i]) {
       const int col = (lane + 32 * i) * 8;
 #pragma unroll
@@ -389,7 +441,7 @@ int launch_embed_fwd(const EmbedArgs& a, cudaStream_t s) {
   const int wpb = 8;
   const long long M = static_cast<long long>(a.B) * a.L;
   LaunchScope scope(CAT_EMBED, 2.0 * M * a.H * 4, s);
-  embed_fwd_kernel<<<static_cast<unsigned>((M + wpb - 1) / wpb), wpb * 32, 0, s>>>(a);
+  VLPK_DISPATCH_NCH(a.H, embed_fwd_kernel<NCH><<<static_cast<unsigned>((M + wpb - 1) / wpb), wpb * 32, 0, s>>>(a));
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -405,11 +457,14 @@ int launch_embed_bwd(const EmbedArgs& a, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(wpb) * 2 * a.H * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    VLPK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    VLPK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    VLPK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    VLPK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
+    VLPK_CUDA(cudaFuncSetAttribute(embed_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 1024 * 4));
     attr_set = true;
   }
   LaunchScope scope(CAT_EMBED, 2.0 * M * a.H * 5, s);
-  embed_bwd_kernel<<<static_cast<unsigned>(grid), wpb * 32, smem, s>>>(a);
+  VLPK_DISPATCH_NCH(a.H, embed_bwd_kernel<NCH><<<static_cast<unsigned>(grid), wpb * 32, smem, s>>>(a));
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -459,29 +514,46 @@ int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients) and fp32 -> bf16 conversion
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* x, long long ld, long long M, int N, int rows_per_blk,
-                                                      float* out) {
-  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (col >= N) return;
-  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_blk;
-  const long long r1 = min(M, r0 + rows_per_blk);
+// Block = 8 column-groups (8 columns = 16 bytes each) x 32 row-lanes over a [COLSUM_ROWS x 64] slab: every 128-byte
+// line is consumed whole by 8 adjacent threads, each thread keeps 8 independent 16-byte loads in flight, and the
+// 32 row-lane partials are folded through shared memory before one atomicAdd per column per block.
+static constexpr int COLSUM_ROWS = 256;
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long M, int N,
+                                                      float* __restrict__ out) {
+  __shared__ float s_part[32][65];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int col = blockIdx.x * 64 + cg * 8;
+  const long long r0 = static_cast<long long>(blockIdx.y) * COLSUM_ROWS;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long r = r0; r < r1; ++r) {
-    float v[8];
-    load8(x + r * ld + col, v);
+  if (col < N) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    for (int i = 0; i < COLSUM_ROWS / 32; ++i) {
+      const long long r = r0 + rl + 32 * i;
+      if (r < M) {
+        float v[8];
+        load8(x + r * ld + col, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v[j];
+      }
+    }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(out + col + j, acc[j]);
+  for (int j = 0; j < 8; ++j) s_part[rl][cg * 8 + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) t += s_part[i][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < N) atomicAdd(out + c, t);
+  }
 }
 
 int launch_colsum(const void* x, long long ld, long long M, int N, float* out, cudaStream_t s) {
   VLPK_CHECK_ARG(N % 8 == 0 && ld % 8 == 0, "colsum: N=%d ld=%lld must be multiples of 8", N, ld);
-  const int rows_per_blk = 32;
-  dim3 grid((N / 8 + 255) / 256, static_cast<unsigned>((M + rows_per_blk - 1) / rows_per_blk));
+  dim3 grid((N + 63) / 64, static_cast<unsigned>((M + COLSUM_ROWS - 1) / COLSUM_ROWS));
   LaunchScope scope(CAT_MISC, 2.0 * M * N, s);
-  colsum_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, M, N, rows_per_blk, out);
+  colsum_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, M, N, out);
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }
