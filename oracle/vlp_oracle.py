@@ -148,7 +148,7 @@ def pretraining_loss(sd, dims, batch, tasks="img2txt", drop_worst_ratio=0.0, p_h
     """BertForPreTrainingLossMask.forward, modeling.py:1033-1143 (mask_image_regions=False branch)."""
     kw = dict(p_hidden=p_hidden, p_attn=p_attn, training=training)
     vis, vpe = region_projections(sd, batch["img"], batch["vis_pe"], p_hidden, training)
-    ext = extended_attention_mask(batch["input_mask"])
+    ext = extended_attention_mask(batch["input_mask"], dtype=vis.dtype)   # parameter dtype, modeling.py:830-831
     emb = embeddings(sd, vis, vpe, batch["input_ids"], batch["segment_ids"], len_vis_input=dims.regions, p=p_hidden, training=training)
     outs = encoder(sd, dims.layers, emb, ext, dims.heads, **kw)
     seq = outs[-1]

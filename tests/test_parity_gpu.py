@@ -50,6 +50,27 @@ def run_model(model, batch, tasks, dtype=torch.bfloat16):
                  mask_image_regions=False, drop_worst_ratio=0.0)
 
 
+def reference_bf16_drift(name):
+    """The reference algorithm's own fp32 -> bf16 drift on the same inputs (oracle run twice on the host CPU): per-parameter
+    gradient rel-L2.  BASELINE.md §3: the kernels' error must stay within 2x of it where it exceeds the flat tolerance."""
+    dims, B, seed, mode, ragged, tasks = mg.CASES[name]
+    out = []
+    for dtype in (torch.float32, torch.bfloat16):
+        sd = {k: v.to(dtype) for k, v in synth.make_state_dict(dims, 0, tasks).items()}
+        sd["cls.predictions.decoder.weight"] = sd["bert.embeddings.word_embeddings.weight"]
+        for k, v in sd.items():
+            if k != "cls.predictions.decoder.weight":
+                v.requires_grad_(True)
+        batch = synth.make_batch(dims, B, seed=seed, mode=mode, ragged=ragged, tasks=tasks)
+        batch = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in batch.items()}
+        losses = O.pretraining_loss(sd, dims, batch, tasks=tasks)
+        sum(l.float().sum() for l in losses).backward()
+        out.append(sd)
+    a, b = out
+    return {k: rel(b[k].grad, a[k].grad) for k in a if a[k].grad is not None and k != "cls.predictions.decoder.weight"
+            and float(a[k].grad.norm()) > 0}
+
+
 def check_loss(got, ref):
     got, ref = float(got), float(ref)
     assert abs(got - ref) <= TOL_LOSS * max(1.0, abs(ref)), (got, ref)
@@ -71,7 +92,9 @@ def test_model_matches_reference_golden(name, golden_dir):
     if tasks != "vqa2":
         assert rel(model.last_prediction_scores, gold["logits"]) < TOL_HID
     sum(l.sum() for l in losses).backward()
+    drift = reference_bf16_drift(name)
     worst = 0.0
+    bad = []
     for k, p in model.named_parameters():
         fp = gold["grads"].get(k)
         if fp is None:
@@ -95,7 +118,11 @@ def test_model_matches_reference_golden(name, golden_dir):
             got = p.grad.detach().float().cpu().flatten()[fp["sample_idx"]]
             r, c = rel(got, fp["sample"]), cosine(got, fp["sample"])
         worst = max(worst, r)
-        assert r < TOL_GRAD and c > 0.999, (k, r, c)
+        tol = max(TOL_GRAD, 2.0 * drift.get(k, 0.0))       # flat tolerance, or 2x the reference's own bf16 drift
+        cos_min = 0.999 if tol == TOL_GRAD and r < 0.0447 else 1.0 - tol * tol  # cos >= 0.999 <=> rel <= 0.0447 for orthogonal error
+        if not (r < tol and c > cos_min):
+            bad.append((k, round(r, 4), round(c, 5), round(drift.get(k, 0.0), 4)))
+    assert not bad, f"{len(bad)} gradient(s) out of tolerance: {bad[:12]}"
     # per-layer outputs (second forward with output_all_encoded_layers=True through BertModel)
     b = {k: v.cuda() for k, v in batch.items()}
     with torch.no_grad():

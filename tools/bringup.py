@@ -214,6 +214,44 @@ def case_attn():
     return ok
 
 
+def case_attn_common_mode():
+    """Numerical stress for the attention backward: keys / values / queries dominated by a component shared by all rows
+    (VLP's 100 near-identical region rows at initialisation) and a gradient that enters at two rows only (the VQA head).
+    The softmax-backward row term must cancel that common mode; compared with fp32 autograd on the same bf16 inputs."""
+    ok = True
+    torch.manual_seed(9)
+    B, heads, Lq, H = 2, 2, 123, 128
+    common = torch.randn(1, 1, 3 * H, device=DEV)
+    qkv = (common * 1.0 + 0.1 * torch.randn(B, Lq, 3 * H, device=DEV)).to(BF)
+    mask = torch.ones(B, Lq, Lq, device=DEV, dtype=torch.int64)
+    bits = _mask_bits(mask)
+    ctx = torch.zeros(B, Lq, H, device=DEV, dtype=BF)
+    lse = torch.zeros(B, heads, Lq, device=DEV)
+    q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+    L.call("vlpk_attn_core_fwd", B, heads, Lq, Lq, q.data_ptr(), 3 * H, k.data_ptr(), v.data_ptr(), 3 * H, bits.data_ptr(), Lq,
+           ctx.data_ptr(), H, lse.data_ptr(), None, 0, L.stream())
+
+    def heads_view(t):
+        return t.float().view(B, Lq, heads, 64).permute(0, 2, 1, 3)
+
+    qf, kf, vf = (heads_view(t).clone().requires_grad_(True) for t in (q, k, v))
+    ref_ctx = _attn_ref(qf, kf, vf, mask).permute(0, 2, 1, 3).reshape(B, Lq, H)
+    ok &= report("common-mode fwd ctx", ctx, ref_ctx)
+    dctx = torch.zeros(B, Lq, H, device=DEV)
+    dctx[:, 0] = torch.randn(B, H, device=DEV)
+    dctx[:, 101] = torch.randn(B, H, device=DEV)
+    dctx = dctx.to(BF)
+    dqkv = torch.zeros(B, Lq, 3 * H, device=DEV, dtype=BF)
+    L.call("vlpk_attn_core_bwd", B, heads, Lq, q.data_ptr(), k.data_ptr(), v.data_ptr(), 3 * H, bits.data_ptr(), Lq, ctx.data_ptr(),
+           dctx.data_ptr(), H, lse.data_ptr(), dqkv.data_ptr(), dqkv[..., H:].data_ptr(), dqkv[..., 2 * H:].data_ptr(), 3 * H, None, 0,
+           L.stream())
+    torch.cuda.synchronize()
+    ref_ctx.backward(dctx.float())
+    for nm, t, g in (("dq", dqkv[..., :H], qf.grad), ("dk", dqkv[..., H:2 * H], kf.grad), ("dv", dqkv[..., 2 * H:], vf.grad)):
+        ok &= report(f"common-mode bwd {nm}", t, g.permute(0, 2, 1, 3).reshape(B, Lq, H), tol=3e-2)
+    return ok
+
+
 def case_rowops():
     ok = True
     torch.manual_seed(5)
@@ -321,7 +359,7 @@ def _perf(extras):
 
 
 CASES = {"gemm_kk": case_gemm_kk, "gemm_epi": case_gemm_epi, "gemm_dgrad": case_gemm_dgrad, "gemm_wgrad": case_gemm_wgrad,
-         "attn": case_attn, "rowops": case_rowops, "perf": case_perf}
+         "attn": case_attn, "attn_common_mode": case_attn_common_mode, "rowops": case_rowops, "perf": case_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

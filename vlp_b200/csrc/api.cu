@@ -53,7 +53,7 @@ int fwd_linear(int M, int N, int K, const void* x, int64_t ldx, const void* w, i
 
 // dx[M,K] = dy[M,N] w[N,K] (+ epilogue with aux)
 int dgrad_linear(int M, int N, int K, const void* dy, int64_t lddy, const void* w, int64_t ldw, void* dx, int64_t lddx, int epi,
-                 const void* aux, int64_t ld_aux, cudaStream_t st) {
+                 const void* aux, int64_t ld_aux, cudaStream_t st, float* colsum = nullptr) {
   GemmDesc g;
   g.M = M; g.N = K; g.K = N;  // contraction over the Linear's output features
   g.A = dy; g.lda = lddy;
@@ -61,6 +61,7 @@ int dgrad_linear(int M, int N, int K, const void* dy, int64_t lddy, const void* 
   g.D0 = dx; g.ldd0 = lddx;
   g.epi = epi;
   g.aux = static_cast<const bf16*>(aux); g.ld_aux = ld_aux;
+  g.colsum = colsum;
   return launch_gemm(g, st);
 }
 
@@ -168,9 +169,8 @@ int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
   const void* dt2 = hdrop ? ws->dt2 : ws->dz2;
   // ---- output.dense: dW2 += dt2^T hmid ; dU = (dt2 W2) * gelu'(u)   [gelu'(u) was stored by the forward epilogue in acts.u]
   VLPK_TRY(wgrad_linear(M, H, I, dt2, H, a->hmid, I, g->w2, I, st));
-  VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, st));
-  // ---- intermediate.dense: db1, dW1 += dU^T y1 ; dy1 = dU W1 + dz2 (residual branch of LN2)
-  VLPK_TRY(launch_colsum(ws->du, I, M, I, g->b1, st));
+  VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, st, g->b1));  // + db1 = column sums of dU
+  // ---- intermediate.dense: dW1 += dU^T y1 ; dy1 = dU W1 + dz2 (residual branch of LN2)
   VLPK_TRY(wgrad_linear(M, I, H, ws->du, I, a->y1, H, g->w1, H, st));
   VLPK_TRY(dgrad_linear(M, I, H, ws->du, I, w->w1, H, ws->dy1, H, EPI_ADD, ws->dz2, H, st));
   // ---- BertSelfOutput: LN1 backward

@@ -6,7 +6,7 @@
 // 128-row UMMA tile, so S and P live only in TMEM / registers / shared memory: the reference's
 // [B,12,L,L] score tensor (written + read ~6x per layer) never touches HBM.
 //
-// One CTA per (head, batch).  4 warps; thread t owns row t of the tile (tcgen05.ld 32x32b layout).
+// One CTA per (head, batch), 8 warps: two threads per tile row (TMEM lane), each owning half of the key columns.
 //   fwd : TMA Q,K,V -> S=QK^T (tcgen05, TMEM) -> scale+bitmask+softmax in registers -> Philox dropout
 //         -> P (bf16, swizzled smem) -> O=PV (tcgen05, V read MN-major straight from its [kv,d] tile)
 //         -> O/rowsum -> TMA store.  Saves only logsumexp per row for backward.
@@ -56,25 +56,29 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], uint32_t mb
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward
+// forward  (256 threads: warp w owns TMEM lane quadrant w & 3 and column half w >> 2; 2 CTAs per SM)
 // ------------------------------------------------------------------------------------------------
+static constexpr int ATT_THREADS = 256;
+
 struct FwdSmem {
   static constexpr int OFF_Q = 0;                 // also O staging
   static constexpr int OFF_K = TILE_B;
   static constexpr int OFF_V = 2 * TILE_B;
   static constexpr int OFF_P = 3 * TILE_B;        // 2 atoms x 16 KB
-  static constexpr int OFF_BAR = 5 * TILE_B;
+  static constexpr int OFF_RED = 5 * TILE_B;      // float[4][128] partial row max / sums exchange
+  static constexpr int OFF_BAR = OFF_RED + 2048;
   static constexpr int TOTAL = OFF_BAR + 64;
   static constexpr int DYN = TOTAL + 1024;
 };
 
-__global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + FwdSmem::OFF_Q;
   uint8_t* sK = smem + FwdSmem::OFF_K;
   uint8_t* sV = smem + FwdSmem::OFF_V;
   uint8_t* sP = smem + FwdSmem::OFF_P;
+  float* s_red = reinterpret_cast<float*>(smem + FwdSmem::OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::OFF_BAR);
   uint64_t* bar_qk = &bars[0];
   uint64_t* bar_v = &bars[1];
@@ -83,8 +87,9 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
 
   const int h = blockIdx.x, b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, hf = warp >> 2;
+  const int row = q4 * 32 + lane;
   const uint64_t dseed = drop_seed(a.drop);
 
   if (tid == 0) {
@@ -123,62 +128,70 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
     umma_commit(bar_s);
   }
 
-  // mask bits for this query row
-  uint32_t mb[4] = {0, 0, 0, 0};
+  // mask bits of this query row for this thread's 64 key columns
+  uint32_t mb[2];
   {
     const int mr = (a.mask_rows == 1) ? 0 : min(row, a.mask_rows - 1);
-    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4));
-    mb[0] = m4.x; mb[1] = m4.y; mb[2] = m4.z; mb[3] = m4.w;
+    const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4 + hf * 2));
+    mb[0] = m2.x; mb[1] = m2.y;
   }
 
   mbar_wait(bar_s, 0);
   __syncwarp();
   tc_fence_after();
-  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t t_lane = static_cast<uint32_t>(q4 * 32) << 16;
 
-  // pass 1: row max (log2 domain)
+  // pass 1: partial row max over this thread's 64 columns (log2 domain), exchanged through shared memory
   float tmax = -INFINITY;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     uint32_t r[32];
     float t[32];
-    tmem_ld32(tS + t_lane + c * 32, r);
+    tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
     tmem_ld_wait();
-    score_chunk(r, mb[c], c * 32, a.Lkv, t);
+    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, t[j]);
   }
-  // pass 2: exponentiate, row sum, dropout, write un-normalised P (bf16) as the A operand of P·V
-  float rsum = 0.f;
+  s_red[hf * 128 + row] = tmax;
+  __syncthreads();
+  tmax = fmaxf(s_red[row], s_red[128 + row]);   // Lkv >= 1 guarantees at least one finite column in half 0
+  __syncthreads();
+  // pass 2: exponentiate, partial row sum, dropout, write un-normalised P (bf16) as the A operand of P·V
+  float rsum = 0.f, lsum = 0.f;
   const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + row) * TL;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     uint32_t r[32];
     float t[32];
-    tmem_ld32(tS + t_lane + c * 32, r);
+    tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
     tmem_ld_wait();
-    score_chunk(r, mb[c], c * 32, a.Lkv, t);
+    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint32_t keep = 0xFFu;
-      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float e0 = exp2f(t[g * 8 + 2 * j] - tmax);
-        const float e1 = exp2f(t[g * 8 + 2 * j + 1] - tmax);
-        rsum += e0 + e1;
+        const float x0 = exp2f(t[g * 8 + 2 * j] - tmax), x1 = exp2f(t[g * 8 + 2 * j + 1] - tmax);
+        lsum += x0 + x1;                                       // exact sum -> logsumexp (backward recomputes P from it)
+        const float e0 = bf16_round(x0), e1 = bf16_round(x1);  // the tensor core sees bf16 P: normalise O by the sum of
+        rsum += e0 + e1;                                       // exactly those values
         const float p0 = ((keep >> (2 * j)) & 1u) ? e0 * a.drop.scale : 0.f;
         const float p1 = ((keep >> (2 * j + 1)) & 1u) ? e1 * a.drop.scale : 0.f;
         pk[j] = pack_bf16x2(p0, p1);
       }
-      const int col = c * 32 + g * 8;
-      sw_write16(sP + (col >> 6) * TILE_B, row, (col & 63) >> 3, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      sw_write16(sP + hf * TILE_B, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
   }
+  s_red[hf * 128 + row] = rsum;
+  s_red[256 + hf * 128 + row] = lsum;
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  rsum = s_red[row] + s_red[128 + row];
+  lsum = s_red[256 + row] + s_red[384 + row];
 
   if (tid == 0) {
     mbar_wait(bar_v, 0);
@@ -190,17 +203,16 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
                umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
     umma_commit(bar_o);
   }
-  if (a.lse != nullptr && row < a.Lq)
-    a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] = (tmax + log2f(rsum)) * LN2;
+  if (hf == 0 && a.lse != nullptr && row < a.Lq)
+    a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] = (tmax + log2f(lsum)) * LN2;
 
   mbar_wait(bar_o, 0);
   __syncwarp();
   tc_fence_after();
   const float inv = 1.0f / rsum;
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
+  {
     uint32_t r[32];
-    tmem_ld32(tO + t_lane + c * 32, r);
+    tmem_ld32(tO + t_lane + hf * 32, r);   // this thread's 32 of the 64 output columns
     tmem_ld_wait();
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -208,7 +220,7 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         pk[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]) * inv, __uint_as_float(r[g * 8 + 2 * j + 1]) * inv);
-      sw_write16(sQ, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));  // Q tile is dead: reuse as staging
+      sw_write16(sQ, row, hf * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));  // Q tile is dead: reuse as staging
     }
   }
   fence_proxy_async_smem();
@@ -227,38 +239,42 @@ __global__ void __launch_bounds__(128, 2) attn_fwd_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward
+// backward  (256 threads, 96 KB smem + 256 TMEM columns -> 2 CTAs per SM)
+//   TMEM: S [0,128) and dP [128,256) are consumed by the softmax-backward phase, then the same columns receive
+//         dV [0,64), dK [64,128), dQ [128,192).   SMEM: one [128 x 128] bf16 buffer holds P (for dV) and then dS (for dK, dQ).
 // ------------------------------------------------------------------------------------------------
 struct BwdSmem {
   static constexpr int OFF_Q = 0;            // later dQ staging
   static constexpr int OFF_K = TILE_B;       // later dK staging
   static constexpr int OFF_V = 2 * TILE_B;   // later dV staging
   static constexpr int OFF_DO = 3 * TILE_B;
-  static constexpr int OFF_P = 4 * TILE_B;   // 2 atoms
-  static constexpr int OFF_DS = 6 * TILE_B;  // 2 atoms
-  static constexpr int OFF_BAR = 8 * TILE_B;
+  static constexpr int OFF_PD = 4 * TILE_B;  // 2 atoms: P, then dS
+  static constexpr int OFF_RED = 6 * TILE_B; // float[2][128] partial delta exchange
+  static constexpr int OFF_BAR = OFF_RED + 1024;
   static constexpr int TOTAL = OFF_BAR + 64;
   static constexpr int DYN = TOTAL + 1024;
 };
 
-__global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + BwdSmem::OFF_Q;
   uint8_t* sK = smem + BwdSmem::OFF_K;
   uint8_t* sV = smem + BwdSmem::OFF_V;
   uint8_t* sdO = smem + BwdSmem::OFF_DO;
-  uint8_t* sP = smem + BwdSmem::OFF_P;
-  uint8_t* sdS = smem + BwdSmem::OFF_DS;
+  uint8_t* sPD = smem + BwdSmem::OFF_PD;
+  float* s_red = reinterpret_cast<float*>(smem + BwdSmem::OFF_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::OFF_BAR);
   uint64_t* bar_in = &bars[0];
   uint64_t* bar_s = &bars[1];
-  uint64_t* bar_o = &bars[2];
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[3]);
+  uint64_t* bar_v = &bars[2];
+  uint64_t* bar_o = &bars[3];
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
 
   const int h = blockIdx.x, b = blockIdx.y;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q4 = warp & 3, hf = warp >> 2;
+  const int row = q4 * 32 + lane;
   const uint64_t dseed = drop_seed(a.drop);
 
   if (tid == 0) {
@@ -268,18 +284,19 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
     tma_prefetch_desc(&tm.o);
     mbar_init(bar_in, 1);
     mbar_init(bar_s, 1);
+    mbar_init(bar_v, 1);
     mbar_init(bar_o, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    tmem_alloc<256>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem, tdK = tmem + 64, tdQ = tmem + 128;
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_in, 4 * TILE_B);
@@ -302,49 +319,61 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
   }
 
   const bool row_ok = row < a.Lq;
-  uint32_t mb[4] = {0, 0, 0, 0};
+  uint32_t mb[2];
   {
     const int mr = (a.mask_rows == 1) ? 0 : min(row, a.mask_rows - 1);
-    const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4));
-    mb[0] = m4.x; mb[1] = m4.y; mb[2] = m4.z; mb[3] = m4.w;
+    const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4 + hf * 2));
+    mb[0] = m2.x; mb[1] = m2.y;
   }
-  // delta_r = sum_d dO[r,d] * O[r,d]  (= sum_j P_rj dP_rj, the softmax-backward row term)
-  float delta = 0.f, lse2 = 0.f;
-  if (row_ok) {
-    const size_t off = (static_cast<size_t>(b) * a.Lq + row) * a.ld_o + h * HD;
-    const uint4* po = reinterpret_cast<const uint4*>(a.o_ptr + off);
-    const uint4* pd = reinterpret_cast<const uint4*>(a.do_ptr + off);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint4 x = __ldg(po + i), y = __ldg(pd + i);
-      const uint32_t xw[4] = {x.x, x.y, x.z, x.w}, yw[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 xf = unpack_bf16x2(xw[j]), yf = unpack_bf16x2(yw[j]);
-        delta += xf.x * yf.x + xf.y * yf.y;
-      }
-    }
-    lse2 = a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] * LOG2E;
-  }
+  const float lse2 = row_ok ? a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] * LOG2E : 0.f;
 
   mbar_wait(bar_s, 0);
   __syncwarp();
   tc_fence_after();
-  const uint32_t t_lane = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t t_lane = static_cast<uint32_t>(q4 * 32) << 16;
   const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + row) * TL;
+  // pass A: delta_r = sum_j P_rj dP_rj with the SAME recomputed P that pass B multiplies with, so that sum_j dS_rj = 0 holds
+  // to fp32 round-off.  (The usual shortcut delta = dO . O inherits the bf16 rounding of O; when keys / values share a large
+  // common component — VLP's 100 near-identical region rows at initialisation — that error is amplified by |mean| / |spread|
+  // and reached 10-20 % in dQ/dK on the VQA parity case.)
+  float delta = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     uint32_t r[32], d[32];
     float t[32];
-    tmem_ld32(tS + t_lane + c * 32, r);
-    tmem_ld32(tdP + t_lane + c * 32, d);
+    tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
+    tmem_ld32(tdP + t_lane + hf * 64 + c * 32, d);
     tmem_ld_wait();
-    score_chunk(r, mb[c], c * 32, a.Lkv, t);
+    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint32_t keep = 0xFFu;
-      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + c * 32 + g * 8) >> 3, a.drop.thresh16);
-      uint32_t pk[4], dk[4];
+      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p = row_ok ? exp2f(t[g * 8 + j] - lse2) : 0.f;
+        const float dpm = ((keep >> j) & 1u) ? __uint_as_float(d[g * 8 + j]) * a.drop.scale : 0.f;
+        delta = fmaf(p, dpm, delta);
+      }
+    }
+  }
+  s_red[hf * 128 + row] = delta;
+  __syncthreads();
+  delta = s_red[row] + s_red[128 + row];
+  uint32_t dsp[32];  // this thread's 64 dS values (bf16 pairs), parked in registers until P has been consumed
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t r[32], d[32];
+    float t[32];
+    tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
+    tmem_ld32(tdP + t_lane + hf * 64 + c * 32, d);
+    tmem_ld_wait();
+    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t keep = 0xFFu;
+      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+      uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float pv[2], dv[2];
@@ -358,56 +387,65 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
           dv[e] = p * (dpm - delta) * 0.125f;
         }
         pk[j] = pack_bf16x2(pv[0], pv[1]);
-        dk[j] = pack_bf16x2(dv[0], dv[1]);
+        dsp[c * 16 + g * 4 + j] = pack_bf16x2(dv[0], dv[1]);
       }
-      const int col = c * 32 + g * 8;
-      sw_write16(sP + (col >> 6) * TILE_B, row, (col & 63) >> 3, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-      sw_write16(sdS + (col >> 6) * TILE_B, row, (col & 63) >> 3, make_uint4(dk[0], dk[1], dk[2], dk[3]));
+      sw_write16(sPD + hf * TILE_B, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
   }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
 
+  constexpr uint32_t idesc_mm = umma_idesc_bf16(128, HD, true, true);   // A^T from [q,kv] tile, B from [q,d] tile
+  constexpr uint32_t idesc_km = umma_idesc_bf16(128, HD, false, true);  // A = dS [q,kv], B from [kv,d] tile
   if (tid == 0) {
     tc_fence_after();
-    constexpr uint32_t idesc_mm = umma_idesc_bf16(128, HD, true, true);   // A^T from [q,kv] tile, B from [q,d] tile
-    constexpr uint32_t idesc_km = umma_idesc_bf16(128, HD, false, true);  // A = dS [q,kv], B from [kv,d] tile
 #pragma unroll
-    for (int k = 0; k < TL / 16; ++k)  // dV[kv,d] = sum_q Pd[q,kv] dO[q,d]
-      umma_f16(tdV, umma_smem_desc_sw128(smem_u32(sP) + k * 2048, TILE_B, 1024),
+    for (int k = 0; k < TL / 16; ++k)  // dV[kv,d] = sum_q Pd[q,kv] dO[q,d]     (overwrites S columns: all S/dP reads are done)
+      umma_f16(tdV, umma_smem_desc_sw128(smem_u32(sPD) + k * 2048, TILE_B, 1024),
                umma_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024), idesc_mm, k > 0 ? 1u : 0u);
+    umma_commit(bar_v);
+  }
+  mbar_wait(bar_v, 0);   // P has been read by the tensor core: the buffer can take dS
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      sw_write16(sPD + hf * TILE_B, row, c * 4 + g,
+                 make_uint4(dsp[c * 16 + g * 4], dsp[c * 16 + g * 4 + 1], dsp[c * 16 + g * 4 + 2], dsp[c * 16 + g * 4 + 3]));
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
 #pragma unroll
     for (int k = 0; k < TL / 16; ++k)  // dK[kv,d] = sum_q dS[q,kv] Q[q,d]
-      umma_f16(tdK, umma_smem_desc_sw128(smem_u32(sdS) + k * 2048, TILE_B, 1024),
+      umma_f16(tdK, umma_smem_desc_sw128(smem_u32(sPD) + k * 2048, TILE_B, 1024),
                umma_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024), idesc_mm, k > 0 ? 1u : 0u);
 #pragma unroll
     for (int k = 0; k < TL / 16; ++k)  // dQ[q,d] = sum_kv dS[q,kv] K[kv,d]
-      umma_f16(tdQ, umma_smem_desc_sw128(smem_u32(sdS) + (k >> 2) * TILE_B + (k & 3) * 32, 16, 1024),
+      umma_f16(tdQ, umma_smem_desc_sw128(smem_u32(sPD) + (k >> 2) * TILE_B + (k & 3) * 32, 16, 1024),
                umma_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024), idesc_km, k > 0 ? 1u : 0u);
     umma_commit(bar_o);
   }
   mbar_wait(bar_o, 0);
   __syncwarp();
   tc_fence_after();
-  // all MMAs retired: Q/K/V tiles are dead, reuse them as output staging
-#pragma unroll 1
+  // all MMAs retired: Q/K/V tiles are dead, reuse them as output staging; each thread converts 32 of the 64 columns
+#pragma unroll
   for (int o = 0; o < 3; ++o) {
     const uint32_t tsrc = (o == 0) ? tdQ : (o == 1 ? tdK : tdV);
     uint8_t* stg = (o == 0) ? sQ : (o == 1 ? sK : sV);
+    uint32_t r[32];
+    tmem_ld32(tsrc + t_lane + hf * 32, r);
+    tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tsrc + t_lane + c * 32, r);
-      tmem_ld_wait();
+    for (int g = 0; g < 4; ++g) {
+      uint32_t pk[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          pk[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
-        sw_write16(stg, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
-      }
+      for (int j = 0; j < 4; ++j) pk[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]), __uint_as_float(r[g * 8 + 2 * j + 1]));
+      sw_write16(stg, row, hf * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
   }
   fence_proxy_async_smem();
@@ -423,7 +461,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_kernel(const __grid_constant_
   tc_fence_after();
   if (warp == 0) {
     __syncwarp();
-    tmem_dealloc<512>(tmem);
+    tmem_dealloc<256>(tmem);
   }
 }
 
@@ -468,7 +506,7 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   LaunchScope scope(CAT_ATTN_FWD, 4.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
-  attn_fwd_kernel<<<dim3(d.heads, d.B), 128, FwdSmem::DYN, stream>>>(tm, a);
+  attn_fwd_kernel<<<dim3(d.heads, d.B), ATT_THREADS, FwdSmem::DYN, stream>>>(tm, a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -501,7 +539,7 @@ int launch_attn_bwd(const AttnDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   LaunchScope scope(CAT_ATTN_BWD, 10.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
-  attn_bwd_kernel<<<dim3(d.heads, d.B), 128, BwdSmem::DYN, stream>>>(tm, a);
+  attn_bwd_kernel<<<dim3(d.heads, d.B), ATT_THREADS, BwdSmem::DYN, stream>>>(tm, a);
   VLPK_CUDA(cudaGetLastError());
   return 0;
 }

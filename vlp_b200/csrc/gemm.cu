@@ -45,6 +45,7 @@ struct GemmArgs {
   long long ld_aux;
   float relu_scale;
   DropoutCfg drop;
+  float* colsum;  // optional [N] fp32: += column sums of the (bf16-rounded) output tile, i.e. the bias gradient of a dgrad output
 };
 
 template <int BN, int CG, int STAGES>
@@ -60,6 +61,13 @@ struct SmemLayout {
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+// Accumulator stage stride / allocation in TMEM columns (allocations must be powers of two: BN = 192 rounds up to 256).
+template <int BN>
+struct TmemGeom {
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int COLS = 2 * ACC_STRIDE;
 };
 
 template <int BN, int CG>
@@ -198,7 +206,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc_cg<2 * BN, CG>(tmem_slot);
+  if (warp == 1) tmem_alloc_cg<TmemGeom<BN>::COLS, CG>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();  // peer barriers must be initialised before any remote arrive / multicast commit
@@ -262,7 +270,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
         const uint32_t acc_phase = (it >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * TmemGeom<BN>::ACC_STRIDE;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -324,7 +332,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
       mbar_wait(&tfull_bar[acc], acc_phase);
       __syncwarp();
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * TmemGeom<BN>::ACC_STRIDE;
 
       if (EPI == EPI_REDUCE_F32) {
         // fp32 staging: 32 columns = 128 bytes per row; one TMA reduce-add box per 32 columns.
@@ -452,6 +460,19 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
               tma_store_2d(&tm.d0, stg, n0 + c * 64, m0);
               tma_store_commit();
             }
+            if (args.colsum != nullptr) {
+              // bias gradient = column sums of this output: fold the staged [128 x 64] bf16 tile (rows beyond M are zero).
+              // Two threads per column take 64 rows each; the buffer is not overwritten before the next-but-one barrier.
+              const int gt = (ew & 3) * 32 + lane;
+              const int col = gt & 63, r0 = (gt >> 6) * 64;
+              float acc_c = 0.f;
+#pragma unroll 8
+              for (int rr = r0; rr < r0 + 64; ++rr) {
+                const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(stg + rr * 128 + (((col >> 3) ^ (rr & 7)) << 4) + (col & 7) * 2);
+                acc_c += __bfloat162float(v);
+              }
+              if (n0 + c * 64 + col < args.N) atomicAdd(args.colsum + n0 + c * 64 + col, acc_c);
+            }
             ++box_seq;
           }
         }
@@ -466,7 +487,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
   tc_fence_after();
   if (warp == 1) {
     __syncwarp();
-    tmem_dealloc_cg<2 * BN, CG>(tmem_base);
+    tmem_dealloc_cg<TmemGeom<BN>::COLS, CG>(tmem_base);
   }
 }
 
@@ -530,6 +551,18 @@ static int dispatch(const GemmDesc& g, const GemmTmaps& tm, const GemmArgs& args
   return -1;
 }
 
+template <int CG>
+static int dispatch_fwd192(const GemmDesc& g, const GemmTmaps& tm, const GemmArgs& args, int num_work, cudaStream_t s) {
+  switch (g.epi) {
+    case EPI_STORE: return launch_inst<192, CG, false, false, EPI_STORE>(tm, args, num_work, s);
+    case EPI_GELU: return launch_inst<192, CG, false, false, EPI_GELU>(tm, args, num_work, s);
+    case EPI_RELU: return launch_inst<192, CG, false, false, EPI_RELU>(tm, args, num_work, s);
+    default: break;
+  }
+  set_error("gemm: 192-wide tile requested for an unsupported epilogue %d", g.epi);
+  return -1;
+}
+
 // Cost model used to pick (tile N, CTA pairing, split-K): rounds of the persistent loop x per-tile cost, where the
 // mainloop cost per k-block is proportional to the operand bytes each SM pulls from L2 (128 rows of A + BN/CG rows of B)
 // and the epilogue cost to the BN columns each CTA drains.
@@ -558,7 +591,8 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   int bn = 128, cg = 1, splits = 1;
   {
     double best = 1e300;
-    for (int cbn : {128, 256}) {
+    for (int cbn : {128, 192, 256}) {
+      if (cbn == 192 && (g.b_mn || g.a_mn)) continue;  // 192-wide tiles are instantiated for forward (K-major) GEMMs only
       if (g.bn != 0 && cbn != g.bn) continue;
       if (g.nseg > 1 && !g.b_mn && seg_rows % cbn != 0) continue;
       for (int ccg : {1, 2}) {
@@ -615,6 +649,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
       tm.d1 = tm.d0;
     }
   }
+  VLPK_CHECK_ARG(g.colsum == nullptr || (!reduce && g.epi != EPI_GELU), "gemm: colsum fusion is for single-output bf16 epilogues");
   if (g.epi == EPI_ADD || g.epi == EPI_MUL || g.epi == EPI_DRELU) {
     VLPK_CHECK_ARG(g.aux != nullptr && (g.ld_aux % 8) == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15u) == 0,
                    "gemm: aux must be 16-byte aligned with ld %% 8 == 0");
@@ -630,11 +665,13 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   a.aux = g.aux;
   a.ld_aux = g.ld_aux;
   a.relu_scale = g.relu_scale;
+  a.colsum = g.colsum;
   a.drop = g.drop;
 
   const int num_m = (g.M + BM * cg - 1) / (BM * cg);
   const int num_n = (g.N + bn - 1) / bn;
   const int num_work = num_m * num_n * splits;
+  if (bn == 192) return cg == 2 ? dispatch_fwd192<2>(g, tm, a, num_work, stream) : dispatch_fwd192<1>(g, tm, a, num_work, stream);
   if (bn == 256 && cg == 2) return dispatch<256, 2>(g, tm, a, num_work, stream);
   if (bn == 256 && cg == 1) return dispatch<256, 1>(g, tm, a, num_work, stream);
   if (bn == 128 && cg == 2) return dispatch<128, 2>(g, tm, a, num_work, stream);

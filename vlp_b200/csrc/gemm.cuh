@@ -41,6 +41,7 @@ struct GemmDesc {
   int epi = EPI_STORE;
   float relu_scale = 1.0f;  // EPI_DRELU: 1/(1-p) of the forward dropout
   DropoutCfg drop = {0.f, 1.f, 0u, 0ull, 0ull, nullptr};
+  float* colsum = nullptr;  // optional [N] fp32: += column sums of the output (bias gradient of a dgrad output)
   int splits = 1;  // split-K (EPI_REDUCE_F32 only); 0 = choose automatically
   int bn = 0;      // tile N (0 = auto)
 };
