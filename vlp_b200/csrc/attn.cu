@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float x0 = exp2f(t[g * 8 + 2 * j] - tmax), x1 = exp2f(t[g * 8 + 2 * j + 1] - tmax);
+        const float x0 = fast_ex2(t[g * 8 + 2 * j] - tmax), x1 = fast_ex2(t[g * 8 + 2 * j + 1] - tmax);
         lsum += x0 + x1;                                       // exact sum -> logsumexp (backward recomputes P from it)
         const float e0 = bf16_round(x0), e1 = bf16_round(x1);  // the tensor core sees bf16 P: normalise O by the sum of
         rsum += e0 + e1;                                       // exactly those values
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
       if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float p = row_ok ? exp2f(t[g * 8 + j] - lse2) : 0.f;
+        const float p = row_ok ? fast_ex2(t[g * 8 + j] - lse2) : 0.f;
         const float dpm = ((keep >> j) & 1u) ? __uint_as_float(d[g * 8 + j]) * a.drop.scale : 0.f;
         delta = fmaf(p, dpm, delta);
       }
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int jj = g * 8 + 2 * j + e;
-          const float p = row_ok ? exp2f(t[jj] - lse2) : 0.f;  // exp2(-inf) = 0 for columns >= Lkv
+          const float p = row_ok ? fast_ex2(t[jj] - lse2) : 0.f;  // exp2(-inf) = 0 for columns >= Lkv
           const bool kp = (keep >> (2 * j + e)) & 1u;
           const float dpm = kp ? __uint_as_float(d[jj]) * a.drop.scale : 0.f;
           pv[e] = kp ? p * a.drop.scale : 0.f;

@@ -217,10 +217,23 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 // below fp32 round-off of the surrounding arithmetic and 4 orders below bf16 resolution); it shares one exp(-x^2/2) with
 // the density term, so the pair costs one MUFU.EX2 + one MUFU.RCP + ~12 FMAs.  (This is the erf form, not the tanh
 // approximation the reference explicitly does not use.)
+// MUFU approximations without the IEEE slow paths the libm-style calls carry (rcp.rn / exp2f expand to a guarded
+// subroutine call per element, which made the GELU epilogue instruction-bound).  ~1 ulp-level error (2^-22 relative).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void gelu_and_grad(float x, float& g, float& d) {
   const float ax = fabsf(x);
-  const float e = __expf(-0.5f * x * x);
-  const float t = __frcp_rn(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
+  const float e = fast_ex2(-0.72134752044448170f * x * x);  // exp(-x^2 / 2)
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -597,7 +597,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
       if (g.nseg > 1 && !g.b_mn && seg_rows % cbn != 0) continue;
       for (int ccg : {1, 2}) {
         if (g_force_cg != 0 && ccg != g_force_cg) continue;
-        if ((cbn / ccg) % 64 != 0) continue;  // a CTA's share of B is made of whole 64-wide boxes
+        if (g.b_mn && (cbn / ccg) % 64 != 0) continue;  // MN-major B: a CTA's share is made of whole 64-wide boxes
         const int max_s = reduce ? (total_kb / 8 > 0 ? total_kb / 8 : 1) : 1;
         for (int s = 1; s <= max_s; ++s) {
           if (reduce && g.splits > 0 && s != (g.splits < max_s ? g.splits : max_s)) continue;

@@ -144,6 +144,7 @@ class EncoderStackFn(torch.autograd.Function):
     def forward(ctx, hidden, mask_bits, cfg, *params):
         n_layers, heads, I, p_attn, p_hidden, training = cfg
         _require_cuda(hidden, "hidden_states")
+        ctx.set_materialize_grads(False)   # unused layer outputs must arrive as None in backward, not as zero tensors
         x = _bf16c(hidden)
         B, Lq, H = x.shape
         pk = [_bf16c(p) for p in params]

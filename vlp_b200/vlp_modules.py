@@ -241,6 +241,7 @@ class BertEncoder(nn.Module):
         super().__init__()
         layer = BertLayer(config)
         self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(config.num_hidden_layers)])
+        self.layers_per_call = None   # None: the whole stack is one fused call; k: groups of k layers (DDP overlap)
 
     def forward(self, hidden_states, attention_mask, prev_embedding=None, prev_encoded_layers=None, output_all_encoded_layers=True):
         assert (prev_embedding is None) == (prev_encoded_layers is None), \
@@ -256,13 +257,21 @@ class BertEncoder(nn.Module):
             if not output_all_encoded_layers:
                 all_layers.append(hidden_states)
             return all_layers
-        # whole stack in one call each way
+        # whole stack in one call each way — or, under data parallelism, in groups of `layers_per_call` layers so that the
+        # gradients of the last group are complete (and their all-reduce bucket can start) while earlier layers still run backward
         bits = _mask_bits(attention_mask)
-        params = []
-        for l in self.layer:
-            params.extend(l.flat_params())
-        outs = ops.EncoderStackFn.apply(hidden_states, bits, self.layer[0]._cfg(len(self.layer)), *params)
+        n = len(self.layer)
+        step = n if not self.layers_per_call else max(1, int(self.layers_per_call))
         dt = hidden_states.dtype
+        outs, cur = [], hidden_states
+        for s in range(0, n, step):
+            group = self.layer[s:s + step]
+            params = []
+            for l in group:
+                params.extend(l.flat_params())
+            g_outs = ops.EncoderStackFn.apply(cur, bits, self.layer[0]._cfg(len(group)), *params)
+            outs.extend(g_outs)
+            cur = g_outs[-1]
         outs = [o if o.dtype == dt else o.to(dt) for o in outs]
         return list(outs) if output_all_encoded_layers else [outs[-1]]
 
@@ -550,7 +559,11 @@ class BertForPreTrainingLossMask(PreTrainedBertModel, _RegionProjections):
             gathered = torch.gather(sequence_output, 1, masked_pos.unsqueeze(2).expand(-1, -1, sequence_output.size(-1)))
             prediction_scores_masked, _ = self.cls(gathered, pooled_output, task_idx=task_idx)
             self.last_prediction_scores = prediction_scores_masked
-            masked_lm_loss = self.crit_mask_lm(prediction_scores_masked.transpose(1, 2).float(), masked_lm_labels)
+            # same per-position CE as crit_mask_lm(scores.transpose(1, 2).float(), labels) (modeling.py:1108-1109), evaluated on the
+            # contiguous [B*P, V] view so that the softmax reduces over the unit-stride dimension
+            V = prediction_scores_masked.size(-1)
+            masked_lm_loss = F.cross_entropy(prediction_scores_masked.reshape(-1, V).float(), masked_lm_labels.reshape(-1),
+                                             reduction="none").view_as(masked_lm_labels)
             masked_lm_loss = loss_mask_and_normalize(masked_lm_loss.float(), masked_weights, drop_worst_ratio)
 
         if mask_image_regions:                               # Selfie-like pretext, modeling.py:1113-1131
