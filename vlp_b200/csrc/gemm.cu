@@ -72,7 +72,8 @@ struct TmemGeom {
 
 template <int BN, int CG>
 struct StageCount {
-  static constexpr int value = (159 * 1024) / (BM * BK * 2 + (BN / CG) * BK * 2);
+  // everything left of the 227 KB after the 4 staging buffers, bias tile, barriers and alignment slack
+  static constexpr int value = (232448 - 1024 - 4 * STG_BYTES - BN * 4 - 256) / (BM * BK * 2 + (BN / CG) * BK * 2);
 };
 
 __device__ __forceinline__ void epi_bar_sync(int group) {
@@ -215,7 +216,9 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
 
   if (warp == 0) {
     // ===================================== TMA producer ========================================
-    if (lane == 0) {
+    // The whole warp walks the loop (all loop state is warp-uniform, so the compiler keeps the TMA operands in uniform
+    // registers); one elected lane issues.  A divergent `if (lane == 0)` body costs an ELECT + R2UR waterfall per instruction.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters) {
@@ -227,27 +230,30 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
         const int m0 = (m_blk * CG + rank) * BM;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sA = smem + stage * L::STAGE_BYTES;
-          uint8_t* sB = sA + L::A_BYTES;
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES * CG);
-          if (!A_MN) {
-            tma_load_2d_cg<CG>(sA, &tm.a, &full_bar[stage], kb * BK, m0);
-          } else {
+          if (elect_one()) {
+            uint8_t* sA = smem + stage * L::STAGE_BYTES;
+            uint8_t* sB = sA + L::A_BYTES;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES * CG);
+            if (!A_MN) {
+              tma_load_2d_cg<CG>(sA, &tm.a, &full_bar[stage], kb * BK, m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg<CG>(sA + j * 8192, &tm.a, &full_bar[stage], m0 + j * 64, kb * BK);
-          }
-          if (!B_MN) {
-            const int n0 = n_blk * BN;
-            const int seg = n0 / args.b_seg_rows;
-            tma_load_2d_cg<CG>(sB, &tm.b[seg], &full_bar[stage], kb * BK, n0 - seg * args.b_seg_rows + rank * (BN / CG));
-          } else {
-            const int k0 = kb * BK;
-            const int seg = k0 / args.b_seg_rows;
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d_cg<CG>(sA + j * 8192, &tm.a, &full_bar[stage], m0 + j * 64, kb * BK);
+            }
+            if (!B_MN) {
+              const int n0 = n_blk * BN;
+              const int seg = n0 / args.b_seg_rows;
+              tma_load_2d_cg<CG>(sB, &tm.b[seg], &full_bar[stage], kb * BK, n0 - seg * args.b_seg_rows + rank * (BN / CG));
+            } else {
+              const int k0 = kb * BK;
+              const int seg = k0 / args.b_seg_rows;
 #pragma unroll
-            for (int j = 0; j < BN / CG / 64; ++j)
-              tma_load_2d_cg<CG>(sB + j * 8192, &tm.b[seg], &full_bar[stage], n_blk * BN + rank * (BN / CG) + j * 64,
-                                 k0 - seg * args.b_seg_rows);
+              for (int j = 0; j < BN / CG / 64; ++j)
+                tma_load_2d_cg<CG>(sB + j * 8192, &tm.b[seg], &full_bar[stage], n_blk * BN + rank * (BN / CG) + j * 64,
+                                   k0 - seg * args.b_seg_rows);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -257,8 +263,15 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
     }
   } else if (warp == 1) {
     // ====================================== MMA issuer ==========================================
-    if (lane == 0 && rank == 0) {
+    // Warp-uniform loop, one elected lane issues the four K=16 MMAs of a k-block and the two commits.  Descriptors are
+    // (constant high word) + (low word = stage base + k * step): one integer add per operand per MMA.
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM * CG, BN, A_MN, B_MN);
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+      constexpr uint32_t A_LBO = A_MN ? (8192u >> 4) : 1u, B_LBO = B_MN ? (8192u >> 4) : 1u;
+      constexpr uint32_t A_KSTEP = A_MN ? (2048u >> 4) : (32u >> 4), B_KSTEP = B_MN ? (2048u >> 4) : (32u >> 4);
+      const uint32_t a_lo0 = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (A_LBO << 16);
+      const uint32_t b_lo0 = a_lo0 - (A_LBO << 16) + (L::A_BYTES >> 4) + (B_LBO << 16);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -274,18 +287,19 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sB = sA + L::A_BYTES;
+          if (elect_one()) {
+            const uint32_t a_lo = a_lo0 + stage * (L::STAGE_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (L::STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: step 16 elements (32 B) inside the swizzle span.  SBO = 8 rows x 128 B.
-            // MN-major: step 16 k-rows (16 x 128 B).  LBO = next 64-wide MN block (one TMA box), SBO = next 8 k-rows.
-            const uint64_t adesc = A_MN ? umma_smem_desc_sw128(sA + k * 2048, 8192, 1024) : umma_smem_desc_sw128(sA + k * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc_sw128(sB + k * 2048, 8192, 1024) : umma_smem_desc_sw128(sB + k * 32, 16, 1024);
-            umma_f16_cg<CG>(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t adesc = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + k * A_KSTEP);
+              const uint64_t bdesc = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + k * B_KSTEP);
+              umma_f16_cg<CG>(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_cg<CG>(&empty_bar[stage]);  // smem slot reusable (in both CTAs) once these MMAs have read it
+            if (kb == kb1 - 1) umma_commit_cg<CG>(&tfull_bar[acc]);
           }
-          umma_commit_cg<CG>(&empty_bar[stage]);  // smem slot reusable (in both CTAs) once these MMAs have read it
-          if (kb == kb1 - 1) umma_commit_cg<CG>(&tfull_bar[acc]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
