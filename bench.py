@@ -205,12 +205,18 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     model, d = build_model(device)
     net = model
+    reducer = None
     if world > 1:
-        # backward in 4 groups of 3 layers (42.5 MB of bf16 gradients each) so that NCCL all-reduces a finished group's bucket
-        # over NVLink while the next group is still computing
-        model.bert.encoder.layers_per_call = 3
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=45,
-                                                        broadcast_buffers=False)
+        # backward runs in 4 groups of 3 layers; each group's gradients are one contiguous bf16 arena (42.5 MB) that is handed to
+        # NCCL (all-reduce AVG over NVLink) as soon as the group finishes, while the next group is still computing.
+        if os.environ.get("VLP_BENCH_DP", "arena") == "torch_ddp":
+            model.bert.encoder.layers_per_call = 3
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=45,
+                                                            broadcast_buffers=False)
+        else:
+            from vlp_b200.dp import GradientAllReducer
+            reducer = GradientAllReducer(model, layers_per_call=3)
+            reducer.broadcast_parameters(0)
     B = PER_GPU_BATCH
     host = synth.make_batch(d, B, seed=1234 + rank, mode="s2s")
 
@@ -232,11 +238,22 @@ def main():
         for i in range(n):
             net.zero_grad(set_to_none=True)
             loss = step_fn(net, get_batch(i))
+            if reducer is not None:
+                reducer.finish()
             if read_loss is not None:
                 read_loss(i, loss)
 
     # ---------------- device-resident timing ("value") ----------------
     run_steps(warmup, lambda i: dev_batch)
+    if world > 1:
+        # after the all-reduce every rank must hold the same averaged gradients (ranks see different data shards)
+        enc = model.bert.encoder.layer
+        chk = torch.stack([enc[0].attention.self.query.weight.grad.float().sum(), enc[11].output.dense.weight.grad.float().sum(),
+                           model.vis_embed[0].weight.grad.float().sum(), model.bert.embeddings.word_embeddings.weight.grad.float().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(torch.equal(allc[0], c) for c in allc), f"gradients differ across ranks after all-reduce: {allc}"
+
     torch.cuda.synchronize()
     barrier()
     launches0 = L.lib().vlpk_launch_count()
@@ -294,7 +311,10 @@ def main():
     t0 = time.perf_counter()
     for i in range(warmup, warmup + args.steps):
         net.zero_grad(set_to_none=True)
-        read_loss(i, step_fn(net, get_e2e_batch(i)))
+        loss_i = step_fn(net, get_e2e_batch(i))
+        if reducer is not None:
+            reducer.finish()
+        read_loss(i, loss_i)
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
     barrier()
@@ -347,7 +367,7 @@ def main():
                                                          if prof[n]["ms_per_step"] > 0 else 0.0)} for n in ("ln_fwd", "ln_bwd")}}
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "seq_len": d.seq_len, "parallelism": f"dp{world}",
+            "config": {"workload": WORKLOAD, "global_batch": B * world, "seq_len": d.seq_len, "parallelism": f"dp{world}" + ("" if world == 1 else (" torch-DDP" if reducer is None else " NCCL all-reduce of flat bf16 gradient arenas overlapped with backward")),
                        "l2": "per-step working set (2.3 GB saved activations + 0.23 GB weights) is far larger than the 126 MB L2; no explicit flush",
                        "timing": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

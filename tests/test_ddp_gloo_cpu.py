@@ -84,6 +84,56 @@ def test_two_rank_gloo_ddp_wrap_and_collective():
     assert res[0][4] == res[1][4]
 
 
+def _reducer_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vlp_b200.dp import GradientAllReducer
+        d = synth.TINY
+        cfg = vm.BertConfig(d.vocab, hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads,
+                            intermediate_size=d.inter, type_vocab_size=d.type_vocab, max_position_embeddings=d.max_pos)
+        torch.manual_seed(rank)
+        model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions)
+        red = GradientAllReducer(model, layers_per_call=1)
+        red.broadcast_parameters(0)
+        w0 = model.bert.encoder.layer[1].output.dense.weight.detach().clone()
+        ref = w0.clone()
+        dist.broadcast(ref, src=0)
+        for p in red.other:
+            p.grad = torch.full_like(p, float(rank + 1))
+        arena = torch.full((1000,), float(rank + 1))           # stands in for an encoder group's flat gradient arena
+        red._on_encoder_grads(arena)
+        red.finish()
+        mean = (world + 1) / 2.0
+        ok = torch.equal(w0, ref) and all(torch.allclose(p.grad, torch.full_like(p, mean)) for p in red.other) and \
+            torch.allclose(arena, torch.full((1000,), mean))
+        enc_ids = {id(p) for p in model.bert.encoder.parameters()}
+        disjoint = all(id(p) not in enc_ids for p in red.other)
+        red.close()
+        q.put((rank, bool(ok), disjoint, model.bert.encoder.layers_per_call))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_arena_reducer():
+    """vlp_b200.dp.GradientAllReducer (what bench.py uses for N > 1): parameter broadcast, mean of the flat encoder arena handed
+    over by the backward hook, mean of the remaining (non-encoder) gradients through one flattened buffer."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, disjoint, lpc in res:
+        assert ok and disjoint and lpc == 1
+
+
 def test_trainable_parameter_count_matches_survey():
     """115 939 396 trainable elements for img2txt BERT-base (the all-reduce payload), pooler included."""
     d = synth.BERT_BASE

@@ -27,6 +27,14 @@ def set_device_seed_tensor(t):
     _seed_dev = t
 
 
+_encoder_grad_hook = None  # data parallelism: callable(flat_gradient_arena) invoked by EncoderStackFn.backward (vlp_b200/dp.py)
+
+
+def set_encoder_grad_hook(fn):
+    global _encoder_grad_hook
+    _encoder_grad_hook = fn
+
+
 def next_seed():
     return (torch.initial_seed() * 1000003 + next(_seed_counter) * 7919) & 0x7FFFFFFFFFFFFFFF
 
@@ -207,6 +215,8 @@ class EncoderStackFn(torch.autograd.Function):
             L.call("vlpk_f32_to_bf16", arena.data_ptr(), garena.data_ptr(), arena.numel(), L.stream())
         else:
             garena = arena
+        if _encoder_grad_hook is not None:
+            _encoder_grad_hook(garena)   # e.g. asynchronous NCCL all-reduce of this group's gradients (dp.GradientAllReducer)
         grads = []
         for i in range(n_layers):
             for v, dt in zip(_grad_views(garena[i], H, I), ctx.param_dtypes[i * PARAMS_PER_LAYER:(i + 1) * PARAMS_PER_LAYER]):
