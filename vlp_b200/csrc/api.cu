@@ -198,9 +198,9 @@ int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
   ad.dq = ws->dqkv; ad.dk = static_cast<bf16*>(ws->dqkv) + H; ad.dv = static_cast<bf16*>(ws->dqkv) + 2 * H;
   ad.ld_dqkv = 3 * H;
   ad.drop = mk_drop(drop, p_attn, site_of(layer_id, SITE_ATTN));
+  ad.dbias = g->bqkv;   // d bqkv = column sums of dQ | dK | dV, folded inside the attention backward kernel
   VLPK_TRY(launch_attn_bwd(ad, st));
-  // ---- QKV projection: d bqkv, dWqkv += dqkv^T x ; dx = dqkv Wqkv + dz1 (residual branch of LN1)
-  VLPK_TRY(launch_colsum(ws->dqkv, 3 * H, M, 3 * H, g->bqkv, st));
+  // ---- QKV projection: dWqkv += dqkv^T x ; dx = dqkv Wqkv + dz1 (residual branch of LN1)
   VLPK_TRY(wgrad_linear(M, 3 * H, H, ws->dqkv, 3 * H, x, H, g->wqkv, H, st));
   GemmDesc d;
   d.M = M; d.N = H; d.K = 3 * H;

@@ -37,6 +37,7 @@ struct AttnArgs {
   const __nv_bfloat16* do_ptr;  // bwd: dO, same layout
   long long ld_o;
   DropoutCfg drop;
+  float* dbias;  // bwd, optional: [3 * heads * 64] fp32, += column sums of dQ | dK | dV (gradient of the q/k/v biases)
 };
 
 __device__ __forceinline__ void sw_write16(uint8_t* tile, int row, int chunk, uint4 v) {
@@ -456,8 +457,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
     tma_store_3d(&tm.dk, sK, h * HD, 0, b);
     tma_store_3d(&tm.dv, sV, h * HD, 0, b);
     tma_store_commit();
-    tma_store_wait<0>();
   }
+  if (a.dbias != nullptr && tid < 192) {
+    // bias gradients of the q/k/v projections = column sums of dQ / dK / dV: fold the staged tiles (rows >= L are exactly zero)
+    const int o = tid >> 6, c = tid & 63;
+    const uint8_t* stg = (o == 0) ? sQ : (o == 1 ? sK : sV);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < TL; ++r)
+      acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + r * 128 + (((c >> 3) ^ (r & 7)) << 4) + (c & 7) * 2));
+    atomicAdd(a.dbias + o * a.heads * HD + h * HD + c, acc);
+  }
+  if (tid == 0) tma_store_wait<0>();
   tc_fence_after();
   if (warp == 0) {
     __syncwarp();
@@ -500,6 +511,7 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
   a.mask_bits = d.mask_bits; a.mask_rows = d.mask_rows;
   a.lse = d.lse; a.o_ptr = nullptr; a.do_ptr = nullptr; a.ld_o = d.ld_o;
   a.drop = d.drop;
+  a.dbias = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     VLPK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::DYN));
@@ -533,6 +545,7 @@ int launch_attn_bwd(const AttnDesc& d, cudaStream_t stream) {
   a.do_ptr = reinterpret_cast<const __nv_bfloat16*>(d.d_o);
   a.ld_o = d.ld_o;
   a.drop = d.drop;
+  a.dbias = d.dbias;
   static bool attr_set = false;
   if (!attr_set) {
     VLPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::DYN));

@@ -24,6 +24,7 @@ struct AttnDesc {
   void* dk = nullptr;
   void* dv = nullptr;  // each [B, L, ld_dqkv]
   int64_t ld_dqkv = 0;
+  float* dbias = nullptr;  // optional [3 * heads * 64] fp32: += column sums of dQ | dK | dV
 };
 
 int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream);
