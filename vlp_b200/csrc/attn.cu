@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
   uint64_t* bar_o = &bars[3];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
 
+  pdl_launch_dependents();
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3, hf = warp >> 2;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem + 128;
+  pdl_wait();
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_qk, 2 * TILE_B);
@@ -272,6 +274,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
   uint64_t* bar_o = &bars[3];
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
 
+  pdl_launch_dependents();
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q4 = warp & 3, hf = warp >> 2;
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem, tdK = tmem + 64, tdQ = tmem + 128;
+  pdl_wait();
 
   if (tid == 0) {
     mbar_arrive_expect_tx(bar_in, 4 * TILE_B);
@@ -518,8 +522,7 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   LaunchScope scope(CAT_ATTN_FWD, 4.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
-  attn_fwd_kernel<<<dim3(d.heads, d.B), ATT_THREADS, FwdSmem::DYN, stream>>>(tm, a);
-  VLPK_CUDA(cudaGetLastError());
+  VLPK_CUDA(launch_ex(attn_fwd_kernel, dim3(d.heads, d.B), dim3(ATT_THREADS), FwdSmem::DYN, stream, 1, tm, a));
   return 0;
 }
 
@@ -552,8 +555,7 @@ int launch_attn_bwd(const AttnDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   LaunchScope scope(CAT_ATTN_BWD, 10.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
-  attn_bwd_kernel<<<dim3(d.heads, d.B), ATT_THREADS, BwdSmem::DYN, stream>>>(tm, a);
-  VLPK_CUDA(cudaGetLastError());
+  VLPK_CUDA(launch_ex(attn_bwd_kernel, dim3(d.heads, d.B), dim3(ATT_THREADS), BwdSmem::DYN, stream, 1, tm, a));
   return 0;
 }
 

@@ -75,6 +75,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while
+// its predecessor drains; everything that touches the predecessor's output must come after pdl_wait() (which returns once
+// the prerequisite grid has completed and its memory is visible).  Both are no-ops for ordinary launches.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor)
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -181,6 +181,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::OFF_TMEM);
   float* s_bias = reinterpret_cast<float*>(smem + L::OFF_BIAS);
 
+  pdl_launch_dependents();  // the next kernel may be scheduled as SMs free up; it blocks in its own pdl_wait()
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
@@ -213,6 +214,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs args) {
   if (CG == 2) cluster_sync_all();  // peer barriers must be initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // barrier init, TMEM allocation and descriptor prefetch above overlap the previous kernel's tail
 
   if (warp == 0) {
     // ===================================== TMA producer ========================================
@@ -523,21 +525,8 @@ static int launch_inst(const GemmTmaps& tm, const GemmArgs& args, int num_work, 
   }
   const int max_clusters = num_sms() / CG;
   const int clusters = num_work < max_clusters ? num_work : max_clusters;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(clusters * CG);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = L::DYN_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
   LaunchScope scope(A_MN ? CAT_GEMM_WGRAD : (B_MN ? CAT_GEMM_DGRAD : CAT_GEMM_FWD), 2.0 * args.M * args.N * args.K, stream);
-  VLPK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tm, args));
+  VLPK_CUDA(launch_ex(kfn, dim3(clusters * CG), dim3(NUM_THREADS), L::DYN_BYTES, stream, CG, tm, args));
   return 0;
 }
 

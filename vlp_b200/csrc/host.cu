@@ -2,6 +2,7 @@
 #include "host.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -69,6 +70,15 @@ int make_tmap(CUtensorMap* out, TmapDtype dt, int rank, const void* base, const 
     return -2;
   }
   return 0;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VLPK_PDL");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int num_sms() {

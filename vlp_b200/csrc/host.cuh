@@ -6,6 +6,8 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
+#include <utility>
 
 namespace vlpk {
 
@@ -54,6 +56,35 @@ inline int make_tmap_2d(CUtensorMap* out, TmapDtype dt, const void* base, uint64
 }
 
 int num_sms();
+
+// Launch with optional cluster dimension and programmatic dependent launch (VLPK_PDL=0 disables the latter).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- launch accounting + optional per-kernel-family timing (CUDA events on the launch stream) ----
 enum KernelCat { CAT_GEMM_FWD = 0, CAT_GEMM_DGRAD, CAT_GEMM_WGRAD, CAT_ATTN_FWD, CAT_ATTN_BWD, CAT_LN_FWD, CAT_LN_BWD, CAT_EMBED,

@@ -70,6 +70,8 @@ __device__ __forceinline__ void row_stats(const float (&z)[NCH][8], const bool (
 // ------------------------------------------------------------------------------------------------
 template <int NCH>
 __global__ void __launch_bounds__(256) ln_res_drop_fwd_kernel(LnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t dseed = drop_seed(a.drop);
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -120,6 +122,8 @@ __device__ __forceinline__ int lnb_idx(int i, int half, int lane) { return ((i *
 
 template <int NCH>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1) ln_res_drop_bwd_kernel(LnArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const uint64_t dseed = drop_seed(a.drop);
   extern __shared__ float s_ln[];       // [LNB_WARPS][3][NCH*256] accumulators, then gamma [NCH*256]
   constexpr int W = NCH * 256;
@@ -260,8 +264,7 @@ int launch_ln_res_drop_fwd(const LnArgs& a, cudaStream_t s) {
   const int wpb = 8;
   const long long grid = (a.M + wpb - 1) / wpb;
   LaunchScope scope(CAT_LN_FWD, 2.0 * a.M * a.H * (a.res ? 3 : 2) + 8.0 * a.M, s);
-  VLPK_DISPATCH_NCH(a.H, ln_res_drop_fwd_kernel<NCH><<<static_cast<unsigned>(grid), wpb * 32, 0, s>>>(a));
-  VLPK_CUDA(cudaGetLastError());
+  VLPK_DISPATCH_NCH(a.H, VLPK_CUDA(launch_ex(ln_res_drop_fwd_kernel<NCH>, dim3(static_cast<unsigned>(grid)), dim3(wpb * 32), 0, s, 1, a)));
   return 0;
 }
 
@@ -281,8 +284,7 @@ int launch_ln_res_drop_bwd(const LnArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   LaunchScope scope(CAT_LN_BWD, 2.0 * a.M * a.H * ((a.res ? 3 : 2) + (a.dz ? 1 : 0) + (a.dt ? 1 : 0)) + 8.0 * a.M, s);
-  VLPK_DISPATCH_NCH(a.H, ln_res_drop_bwd_kernel<NCH><<<static_cast<unsigned>(grid), LNB_WARPS * 32, smem, s>>>(a));
-  VLPK_CUDA(cudaGetLastError());
+  VLPK_DISPATCH_NCH(a.H, VLPK_CUDA(launch_ex(ln_res_drop_bwd_kernel<NCH>, dim3(static_cast<unsigned>(grid)), dim3(LNB_WARPS * 32), smem, s, 1, a)));
   return 0;
 }
 
