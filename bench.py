@@ -355,8 +355,13 @@ def main():
     peak_tf = peaks["bf16_tflops_sustained"]
     fl = synth.flops_per_sample()
     step_tf = value / world * fl["total"] / 1e12
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj["gemm_dram_bytes_per_launch_avg"], tj["source"]
     roofline = {"bound": "tensor", "kernel": "vlpk::gemm_kernel (tcgen05 GEMM family: fwd/dgrad/wgrad)", "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                 "launches_per_step": gemm_n, "flops_per_launch_avg": gemm_fl / max(gemm_n, 1), "avg_launch_us": gemm_ms * 1e3 / max(gemm_n, 1),
                 "gemm_share_of_step": gemm_ms / ms_per_step,
