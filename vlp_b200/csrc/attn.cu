@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
   // common component — VLP's 100 near-identical region rows at initialisation — that error is amplified by |mean| / |spread|
   // and reached 10-20 % in dQ/dK on the VQA parity case.)
   float delta = 0.f;
+  uint32_t kb0 = 0xFFFFFFFFu, kb1 = 0xFFFFFFFFu;  // dropout keep mask of this thread's 64 columns (Philox evaluated once)
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
     uint32_t r[32], d[32];
@@ -350,10 +351,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
     tmem_ld32(tdP + t_lane + hf * 64 + c * 32, d);
     tmem_ld_wait();
     score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+    uint32_t kbc = 0xFFFFFFFFu;
+    if (a.drop.p > 0.f) {
+      kbc = 0u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        kbc |= dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16) << (8 * g);
+    }
+    if (c == 0) kb0 = kbc; else kb1 = kbc;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint32_t keep = 0xFFu;
-      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+      const uint32_t keep = (kbc >> (8 * g)) & 0xFFu;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float p = row_ok ? fast_ex2(t[g * 8 + j] - lse2) : 0.f;
@@ -376,8 +384,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
     score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint32_t keep = 0xFFu;
-      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
+      const uint32_t keep = ((c == 0 ? kb0 : kb1) >> (8 * g)) & 0xFFu;
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
