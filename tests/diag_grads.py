@@ -1,5 +1,5 @@
 """Diagnostic: per-parameter gradient error of the GPU path vs the fp32 oracle (run live), plus the per-row error of the
-gradient flowing into the embedding output.  python tools/diag_grads.py [case ...]"""
+gradient flowing into the embedding output.  python tests/diag_grads.py [case ...]"""
 import os
 import sys
 
