@@ -104,6 +104,8 @@ int vlpk_version(void);
 const char* vlpk_last_error(void);
 /* bring-up / A-B testing only: force the GEMM CTA-group size (0 = cost model, 1 = single CTA tiles, 2 = CTA pairs). */
 void vlpk_debug_set_cta_group(int cg);
+/* host-only: the (tile N, CTA-group size, split-K) the cost model picks for a GEMM; out3 = {bn, cg, splits}.  No GPU needed. */
+int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int seg_rows, int epi, int bn, int splits, int* out3);
 
 /* get_extended_attention_mask (modeling.py:807-833) -> per-row 128-bit "attend" bitmask.
  * mask: [B, rows, kv] with element strides (stride_b, stride_r, 1); rows may be 1 (2-D mask). out: [B, rows, 4] u32. */

@@ -89,3 +89,77 @@ def test_install_shadows_reference_import_path():
 def test_flop_model_matches_baseline_md():
     f = synth.flops_per_sample()
     assert abs(f["fwd"] / 1e9 - 22.989) < 0.01 and abs(f["total"] / 1e9 - 67.881) < 0.02
+
+
+def test_from_pretrained_remaps_match_live_reference(tmp_path):
+    """from_pretrained keeps the reference's kwargs and checkpoint remaps (modeling.py:554-764): TF-era gamma/beta names, growing the
+    segment-type table 2 -> 6 (rows 2,3,4 <- row 0, row 5 <- row 1) and tiling a longer position table.  Compared, parameter by
+    parameter, with the unmodified reference's from_pretrained on the same checkpoint (build container only)."""
+    import json
+    import pickle
+
+    import numpy as np
+
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("/root/reference not present")
+    d = synth.VlpDims(vocab=300, hidden=128, layers=1, heads=2, inter=256, type_vocab=2, max_pos=64, regions=100, text=20)
+    sd = synth.make_state_dict(d, 5)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for old, new in (("bert.embeddings.LayerNorm.weight", "bert.embeddings.LayerNorm.gamma"),
+                     ("bert.embeddings.LayerNorm.bias", "bert.embeddings.LayerNorm.beta")):
+        sd[new] = sd.pop(old)
+    cfg = {"vocab_size": d.vocab, "hidden_size": d.hidden, "num_hidden_layers": d.layers, "num_attention_heads": d.heads,
+           "intermediate_size": d.inter, "hidden_act": "gelu", "hidden_dropout_prob": 0.1, "attention_probs_dropout_prob": 0.1,
+           "max_position_embeddings": d.max_pos, "type_vocab_size": 2, "initializer_range": 0.02}
+    (tmp_path / "bert_config.json").write_text(json.dumps(cfg))
+    (tmp_path / "detectron_weights").mkdir()
+    pickle.dump(np.zeros((2048, 2048), np.float32), open(tmp_path / "detectron_weights" / "fc7_w.pkl", "wb"))
+    pickle.dump(np.zeros((2048,), np.float32), open(tmp_path / "detectron_weights" / "fc7_b.pkl", "wb"))
+    kw = dict(type_vocab_size=6, max_position_embeddings=128, enable_butd=True, len_vis_input=100, tasks="img2txt")
+    mine = vm.BertForPreTrainingLossMask.from_pretrained(str(tmp_path), state_dict={k: v.clone() for k, v in sd.items()}, **kw)
+    m = ref_shim.import_reference_modeling()
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        ref = m.BertForPreTrainingLossMask.from_pretrained(str(tmp_path), state_dict={k: v.clone() for k, v in sd.items()},
+                                                           relax_projection=0, fp32_embedding=False, **kw)
+    finally:
+        os.chdir(cwd)
+    a, b = mine.state_dict(), ref.state_dict()
+    assert set(a.keys()) == set(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape, k
+        assert torch.equal(a[k], b[k]), k
+    assert a["bert.embeddings.token_type_embeddings.weight"].shape[0] == 6
+    assert torch.equal(a["bert.embeddings.position_embeddings.weight"][64:], a["bert.embeddings.position_embeddings.weight"][:64])
+
+
+def _plan(M, N, K, a_mn=0, b_mn=0, nseg=1, seg_rows=0, epi=0, bn=0, splits=1):
+    import ctypes as C
+    out = (C.c_int * 3)()
+    rc = _lib.lib().vlpk_debug_plan_gemm(M, N, K, a_mn, b_mn, nseg, seg_rows, epi, bn, splits, out)
+    assert rc == 0, _lib.lib().vlpk_last_error()
+    return tuple(out)
+
+
+def test_gemm_plan_for_the_hot_shapes():
+    """Host-side tile planning (csrc/gemm.cu plan_gemm; 148 SMs assumed when no device is visible).  These are the configurations the
+    B200 profile in profiles/r01_launches_final.md ran with: pins the cost model against silent drift."""
+    M = 64 * 123
+    assert _plan(M, 2304, 768, nseg=3, seg_rows=768)[:2] == (256, 2)          # packed QKV projection
+    assert _plan(M, 768, 768)[:2] == (192, 2)                                  # attention.output.dense
+    assert _plan(M, 3072, 768, epi=1)[:2] == (256, 2)                          # intermediate.dense + GELU
+    assert _plan(M, 768, 3072)[:2] == (192, 2)                                 # output.dense
+    assert _plan(M, 3072, 768, b_mn=1, epi=4)[:2] == (256, 2)                  # dgrad through GELU
+    assert _plan(M, 768, 3072, b_mn=1, epi=3)[:2] == (256, 2)                  # dgrad + residual gradient
+    assert _plan(M, 768, 2304, b_mn=1, nseg=3, seg_rows=768, epi=3)[:2] == (256, 2)
+    for (n, k) in ((768, 3072), (3072, 768), (2304, 768), (768, 768)):         # weight gradients: split-K fills the machine
+        bn, cg, s = _plan(n, k, M, a_mn=1, b_mn=1, epi=6, splits=0)
+        tiles = ((n + 128 * cg - 1) // (128 * cg)) * ((k + bn - 1) // bn) * s
+        assert cg == 2 and s >= 2 and 60 <= tiles <= 2 * 74
+        assert (123 + s - 1) // s >= 8                                         # at least 8 k-blocks per work item
+    # MN-major B never gets a tile whose per-CTA share is not whole 64-wide boxes; forced shapes are honoured
+    assert _plan(M, 768, 768, b_mn=1)[0] in (128, 256)
+    assert _plan(M, 768, 768, bn=128)[0] == 128
+    assert _plan(300, 256, 192, bn=256)[:2][0] == 256

@@ -254,6 +254,14 @@ extern "C" {
 
 int vlpk_version(void) { return VLPK_VERSION; }
 void vlpk_debug_set_cta_group(int cg) { debug_set_cta_group(cg); }
+int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int seg_rows, int epi, int bn, int splits, int* out3) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K;
+  g.a_mn = a_mn != 0; g.b_mn = b_mn != 0;
+  g.nseg = nseg; g.b_seg_rows = seg_rows;
+  g.epi = epi; g.bn = bn; g.splits = splits;
+  return plan_gemm(g, &out3[0], &out3[1], &out3[2]);
+}
 const char* vlpk_last_error(void) { return get_error(); }
 
 int vlpk_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, int64_t stride_b, int64_t stride_r, uint32_t* out,

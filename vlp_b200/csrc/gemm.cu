@@ -581,16 +581,11 @@ static double tile_cost(int M, int N, int total_kb, int bn, int cg, int splits, 
   return rounds * (mainloop + epi + 60.0);
 }
 
-int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
-  VLPK_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  VLPK_CHECK_ARG(g.N % 8 == 0, "gemm: N=%d must be a multiple of 8", g.N);
-  VLPK_CHECK_ARG(g.nseg >= 1 && g.nseg <= 3, "gemm: nseg=%d", g.nseg);
+// Tile N, CTA-group size and split-K for one GEMM (pure host logic; exposed to the CPU tests as vlpk_debug_plan_gemm).
+int plan_gemm(const GemmDesc& g, int* bn_out, int* cg_out, int* splits_out) {
   const int seg_rows = g.nseg > 1 ? g.b_seg_rows : (g.b_mn ? g.K : g.N);
   const int total_kb = (g.K + BK - 1) / BK;
   const bool reduce = (g.epi == EPI_REDUCE_F32);
-  VLPK_CHECK_ARG(g.splits <= 1 || reduce, "gemm: split-K needs EPI_REDUCE_F32");
-
-  // ---- choose tile N, CTA-group size and split-K
   int bn = 128, cg = 1, splits = 1;
   {
     double best = 1e300;
@@ -622,6 +617,23 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
     const int kb_per = (total_kb + splits - 1) / splits;
     splits = (total_kb + kb_per - 1) / kb_per;  // no empty splits
   }
+  *bn_out = bn;
+  *cg_out = cg;
+  *splits_out = splits;
+  return 0;
+}
+
+int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
+  VLPK_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  VLPK_CHECK_ARG(g.N % 8 == 0, "gemm: N=%d must be a multiple of 8", g.N);
+  VLPK_CHECK_ARG(g.nseg >= 1 && g.nseg <= 3, "gemm: nseg=%d", g.nseg);
+  const int seg_rows = g.nseg > 1 ? g.b_seg_rows : (g.b_mn ? g.K : g.N);
+  const bool reduce = (g.epi == EPI_REDUCE_F32);
+  VLPK_CHECK_ARG(g.splits <= 1 || reduce, "gemm: split-K needs EPI_REDUCE_F32");
+
+  // ---- choose tile N, CTA-group size and split-K
+  int bn = 128, cg = 1, splits = 1;
+  VLPK_TRY(plan_gemm(g, &bn, &cg, &splits));
 
   GemmTmaps tm;
   memset(&tm, 0, sizeof(tm));

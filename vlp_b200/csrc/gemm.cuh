@@ -49,5 +49,6 @@ struct GemmDesc {
 // Returns 0 on success, <0 on argument error, >0 cudaError_t.  Message via vlpk::set_error.
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
 void debug_set_cta_group(int cg);
+int plan_gemm(const GemmDesc& g, int* bn_out, int* cg_out, int* splits_out);
 
 }  // namespace vlpk
