@@ -19,6 +19,7 @@
 #ifndef VLPK_H_
 #define VLPK_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -164,6 +165,24 @@ int vlpk_layer_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
 int vlpk_layer_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits, int mask_rows,
                    const VlpkLayerActs* a, const void* dy, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws,
                    float p_attn, float p_hidden, const VlpkDropout* drop, uint64_t layer_id, void* stream);
+
+/* The two halves of vlpk_layer_bwd, for callers that keep BertAttention / BertIntermediate+BertOutput as separate autograd nodes.
+ * vlpk_ffn_bwd: dy = gradient of a->y -> dy1 = gradient of a->y1 (may alias dy); accumulates w1,b1,w2,b2,ln2 gradients.
+ * vlpk_mha_bwd: dy1 = gradient of a->y1 -> dx = gradient of x (may alias dy1); accumulates wqkv,bqkv,wo,bo,ln1 gradients.
+ * vlpk_layer_bwd(dy, dx) == vlpk_ffn_bwd(dy, ws->dy1) followed by vlpk_mha_bwd(ws->dy1, dx). */
+int vlpk_ffn_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const VlpkLayerActs* a, const void* dy, void* dy1,
+                 const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_hidden, const VlpkDropout* drop, uint64_t layer_id,
+                 void* stream);
+int vlpk_mha_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits, int mask_rows,
+                 const VlpkLayerActs* a, const void* dy1, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_attn,
+                 float p_hidden, const VlpkDropout* drop, uint64_t layer_id, void* stream);
+/* BertAttention.forward with history_states (modeling.py:273-277; BertModelIncr / BertForSeq2SeqDecoder, :856-875, 1189-1253):
+ * inference only (no dropout, nothing saved for backward).  x: [B*Lq,H] new rows; x_kv = cat(history, x): [B*Lkv,H]. */
+int vlpk_mha_incr_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* mask_bits,
+                      int mask_rows, VlpkLayerActs* a, uint64_t layer_id, void* stream);
+/* Host-only: bytes the caller must provide for a shape.  out3 = { all VlpkLayerActs buffers of ONE layer,
+ * all VlpkBwdScratch buffers (shared by the layers), the fp32 VlpkLayerGrads accumulators of ONE layer }. */
+int vlpk_workspace_bytes(const VlpkShape* s, size_t* out3);
 
 /* BertEncoder.forward (modeling.py:382-402): n_layers x BertLayer in one host call.  acts[i].y is layer i's output. */
 int vlpk_encoder_fwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits,

@@ -163,3 +163,86 @@ def test_gemm_plan_for_the_hot_shapes():
     assert _plan(M, 768, 768, b_mn=1)[0] in (128, 256)
     assert _plan(M, 768, 768, bn=128)[0] == 128
     assert _plan(300, 256, 192, bn=256)[:2][0] == 256
+
+
+def test_workspace_bytes_matches_the_python_allocations():
+    """vlpk_workspace_bytes (host-only) vs what vlp_b200/ops.py allocates for the same shape."""
+    import ctypes as C
+    from vlp_b200 import ops
+    for (B, Lq, Lkv, H, heads, I) in ((2, 15, 15, 128, 2, 512), (64, 123, 123, 768, 12, 3072), (3, 2, 77, 128, 2, 512)):
+        out = (C.c_size_t * 3)()
+        shape = _lib.VlpkShape(B, Lq, Lkv, H, heads, I)
+        assert _lib.lib().vlpk_workspace_bytes(C.byref(shape), out) == 0
+        M = B * Lq
+        bf = M * 3 * H + 5 * M * H + 2 * M * I + (B * Lkv * 2 * H if Lkv != Lq else 0)
+        f32 = B * heads * Lq + 4 * M
+        assert out[0] == 2 * bf + 4 * f32
+        assert out[1] == 2 * (7 * M * H + M * I + 3 * M * H)
+        assert out[2] == 4 * sum(ops._layer_sizes(H, I))
+    if True:                                                   # the same numbers from a live (CPU-allocated) _Acts
+        a = ops._Acts(1, 2, 15, 128, 2, 512, "cpu")
+        shape = _lib.VlpkShape(2, 15, 15, 128, 2, 512)
+        _lib.lib().vlpk_workspace_bytes(C.byref(shape), out)
+        assert out[0] == a.bf.numel() * 2 + a.f32.numel() * 4
+    bad = _lib.VlpkShape(2, 129, 129, 128, 2, 512)
+    assert _lib.lib().vlpk_workspace_bytes(C.byref(bad), out) < 0 and b"sequence length" in _lib.lib().vlpk_last_error()
+
+
+def test_gpu_case_marshalling_dry_run():
+    """The C-ABI call sequences of tests/test_abi_split_gpu.py, converted against the declared prototypes on CPU (nothing runs)."""
+    from tools import abi_cases
+    with abi_cases.dry_run() as calls:
+        abi_cases.split_backward_case("cpu")
+        abi_cases.incremental_case("cpu")
+    assert calls == ["vlpk_mask_pack", "vlpk_layer_fwd", "vlpk_layer_bwd", "vlpk_ffn_bwd", "vlpk_mha_bwd",
+                     "vlpk_mask_pack", "vlpk_mha_fwd", "vlpk_mha_incr_fwd"]
+
+
+def _tiny_config(drop=0.1):
+    d = synth.TINY
+    return d, vm.BertConfig(d.vocab, hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads,
+                            intermediate_size=d.inter, type_vocab_size=d.type_vocab, max_position_embeddings=d.max_pos,
+                            hidden_dropout_prob=drop, attention_probs_dropout_prob=drop)
+
+
+def test_training_step_marshalling_dry_run():
+    """One forward + backward of BertForPreTrainingLossMask with the library call replaced by prototype conversion: the whole
+    Python side of the hot path (autograd Functions, struct filling, argument order) runs on CPU; values are meaningless."""
+    from tools import abi_cases
+    d, cfg = _tiny_config()
+    model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions).bfloat16().train()
+    b = synth.make_batch(d, 2, seed=1)
+    with abi_cases.dry_run() as calls:
+        out = model(b["img"].bfloat16(), b["vis_pe"].bfloat16(), b["input_ids"], b["segment_ids"], b["input_mask"], b["masked_ids"], None,
+                    b["is_next"], masked_pos=b["masked_pos"], masked_weights=b["masked_weights"], task_idx=b["task_idx"],
+                    vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
+        sum(l.float().sum() for l in out).backward()
+    assert calls == ["vlpk_linear_fwd"] * 3 + ["vlpk_embed_fwd", "vlpk_mask_pack", "vlpk_encoder_fwd", "vlpk_encoder_bwd", "vlpk_f32_to_bf16",
+                     "vlpk_embed_bwd"] + ["vlpk_linear_bwd"] * 3
+    missing = [n for n, p in model.named_parameters() if p.grad is None]
+    assert all(n.startswith("bert.pooler.") for n in missing), missing      # the img2txt loss never touches the pooler
+    for n, p in model.named_parameters():
+        if p.grad is not None:
+            assert p.grad.shape == p.shape and p.grad.dtype == p.dtype, n
+
+
+def test_greedy_decode_marshalling_dry_run():
+    """BertForSeq2SeqDecoder's incremental loop (q_len != kv_len calls into vlpk_layer_fwd) under the same dry-run."""
+    from tools import abi_cases
+    d, cfg = _tiny_config(0.0)
+    R, L = d.regions, d.seq_len
+    model = vm.BertForSeq2SeqDecoder(cfg, mask_word_id=103, eos_id=102, search_beam_size=1, enable_butd=True, len_vis_input=R).bfloat16().eval()
+    B = 2
+    input_ids = torch.tensor([[101] + [100] * R + [102]] * B)
+    tt = torch.tensor([[4] * (R + 2) + [5] * (L - R - 2)] * B)
+    pos = torch.arange(L).unsqueeze(0).expand(B, L).contiguous()
+    mask = torch.zeros(B, L, L, dtype=torch.long)
+    mask[:, :, :R + 2] = 1
+    mask[:, R + 2:, R + 2:] = torch.tril(torch.ones(L - R - 2, L - R - 2, dtype=torch.long))
+    with abi_cases.dry_run() as calls:
+        ids, scores = model(torch.randn(B, R, d.vis_dim).bfloat16(), torch.randn(B, R, d.pe_dim).bfloat16(), input_ids, tt, pos, mask,
+                            task_idx=None, sample_mode="greedy")
+    steps = L - R - 2
+    assert ids.shape == (B, steps)
+    assert calls.count("vlpk_layer_fwd") + calls.count("vlpk_encoder_fwd") * cfg.num_hidden_layers >= steps * cfg.num_hidden_layers
+    assert calls.count("vlpk_embed_fwd") == steps and "vlpk_encoder_bwd" not in calls

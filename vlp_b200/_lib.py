@@ -76,6 +76,14 @@ _SIGS = {
     "vlpk_layer_bwd": (c_int, [C.POINTER(VlpkShape), C.POINTER(VlpkLayerWeights), _P, _P, c_int, C.POINTER(VlpkLayerActs), _P, _P,
                                C.POINTER(VlpkLayerGrads), C.POINTER(VlpkBwdScratch), c_float, c_float, C.POINTER(VlpkDropout),
                                c_u64, _P]),
+    "vlpk_ffn_bwd": (c_int, [C.POINTER(VlpkShape), C.POINTER(VlpkLayerWeights), C.POINTER(VlpkLayerActs), _P, _P,
+                             C.POINTER(VlpkLayerGrads), C.POINTER(VlpkBwdScratch), c_float, C.POINTER(VlpkDropout), c_u64, _P]),
+    "vlpk_mha_bwd": (c_int, [C.POINTER(VlpkShape), C.POINTER(VlpkLayerWeights), _P, _P, c_int, C.POINTER(VlpkLayerActs), _P, _P,
+                             C.POINTER(VlpkLayerGrads), C.POINTER(VlpkBwdScratch), c_float, c_float, C.POINTER(VlpkDropout),
+                             c_u64, _P]),
+    "vlpk_mha_incr_fwd": (c_int, [C.POINTER(VlpkShape), C.POINTER(VlpkLayerWeights), _P, _P, _P, c_int,
+                                  C.POINTER(VlpkLayerActs), c_u64, _P]),
+    "vlpk_workspace_bytes": (c_int, [C.POINTER(VlpkShape), C.POINTER(C.c_size_t)]),
     "vlpk_encoder_fwd": (c_int, [C.POINTER(VlpkShape), c_int, C.POINTER(VlpkLayerWeights), _P, _P, c_int,
                                  C.POINTER(VlpkLayerActs), c_float, c_float, C.POINTER(VlpkDropout), _P]),
     "vlpk_encoder_bwd": (c_int, [C.POINTER(VlpkShape), c_int, C.POINTER(VlpkLayerWeights), _P, _P, c_int,

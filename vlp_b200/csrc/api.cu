@@ -149,10 +149,12 @@ int ffn_fwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, VlpkLayerActs* a
   return launch_ln_res_drop_fwd(ln, st);
 }
 
-int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* bits, int mask_rows,
-                   const VlpkLayerActs* a, const void* dy, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_attn,
-                   float p_hidden, const VlpkDropout* drop, uint64_t layer_id, cudaStream_t st) {
-  VLPK_CHECK_ARG(s->Lq == s->Lkv, "layer_bwd: training path requires Lq == Lkv");
+// Backward of BertIntermediate + BertOutput.  dy: gradient of a->y; dy1: receives the gradient of a->y1 (both branches: through
+// the two Linears and through LN2's residual input).  dy1 may alias dy (dy is consumed by the first kernel only).
+int ffn_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const VlpkLayerActs* a, const void* dy, void* dy1,
+                 const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_hidden, const VlpkDropout* drop, uint64_t layer_id,
+                 cudaStream_t st) {
+  VLPK_CHECK_ARG(s->Lq == s->Lkv, "ffn_bwd: training path requires Lq == Lkv");
   const int H = s->H, I = s->I, M = s->B * s->Lq;
   const bool hdrop = (drop != nullptr && p_hidden > 0.f);
   // ---- BertOutput: LN2 backward (also yields d b2 as the column sum of dt2)
@@ -172,13 +174,23 @@ int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
   VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, st, g->b1));  // + db1 = column sums of dU
   // ---- intermediate.dense: dW1 += dU^T y1 ; dy1 = dU W1 + dz2 (residual branch of LN2)
   VLPK_TRY(wgrad_linear(M, I, H, ws->du, I, a->y1, H, g->w1, H, st));
-  VLPK_TRY(dgrad_linear(M, I, H, ws->du, I, w->w1, H, ws->dy1, H, EPI_ADD, ws->dz2, H, st));
+  return dgrad_linear(M, I, H, ws->du, I, w->w1, H, dy1, H, EPI_ADD, ws->dz2, H, st);
+}
+
+// Backward of BertAttention.  dy1: gradient of a->y1; dx: receives the gradient of the layer input x (attention branch +
+// LN1's residual input).  dx may alias dy1.
+int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* bits, int mask_rows,
+                 const VlpkLayerActs* a, const void* dy1, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_attn,
+                 float p_hidden, const VlpkDropout* drop, uint64_t layer_id, cudaStream_t st) {
+  VLPK_CHECK_ARG(s->Lq == s->Lkv, "mha_bwd: training path requires Lq == Lkv");
+  const int H = s->H, M = s->B * s->Lq;
+  const bool hdrop = (drop != nullptr && p_hidden > 0.f);
   // ---- BertSelfOutput: LN1 backward
   LnArgs l1;
   l1.M = M; l1.H = H;
   l1.t = static_cast<const bf16*>(a->t1); l1.res = static_cast<const bf16*>(x);
   l1.gamma = static_cast<const bf16*>(w->ln1_g); l1.stats = reinterpret_cast<float2*>(a->stats1);
-  l1.dy = static_cast<const bf16*>(ws->dy1);
+  l1.dy = static_cast<const bf16*>(dy1);
   l1.dz = static_cast<bf16*>(ws->dz1);
   l1.dt = hdrop ? static_cast<bf16*>(ws->dt1) : nullptr;
   l1.dgamma = g->ln1_g; l1.dbeta = g->ln1_b; l1.dbias = g->bo;
@@ -211,6 +223,13 @@ int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
   d.epi = EPI_ADD;
   d.aux = static_cast<const bf16*>(ws->dz1); d.ld_aux = H;
   return launch_gemm(d, st);
+}
+
+int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* bits, int mask_rows,
+                   const VlpkLayerActs* a, const void* dy, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_attn,
+                   float p_hidden, const VlpkDropout* drop, uint64_t layer_id, cudaStream_t st) {
+  VLPK_TRY(ffn_bwd_impl(s, w, a, dy, ws->dy1, g, ws, p_hidden, drop, layer_id, st));
+  return mha_bwd_impl(s, w, x, bits, mask_rows, a, ws->dy1, dx, g, ws, p_attn, p_hidden, drop, layer_id, st);
 }
 
 __global__ void add_bf16_kernel(bf16* __restrict__ dst, const bf16* __restrict__ a, const bf16* __restrict__ b, long long n) {
@@ -426,6 +445,40 @@ int vlpk_layer_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x,
   VLPK_TRY(check_shape(s));
   VLPK_CHECK_ARG(w && x && mask_bits && a && dy && dx && g && ws, "layer_bwd: null pointer");
   return layer_bwd_impl(s, w, x, mask_bits, mask_rows, a, dy, dx, g, ws, p_attn, p_hidden, drop, layer_id, S(stream));
+}
+
+int vlpk_ffn_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const VlpkLayerActs* a, const void* dy, void* dy1,
+                 const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_hidden, const VlpkDropout* drop, uint64_t layer_id,
+                 void* stream) {
+  VLPK_TRY(check_shape(s));
+  VLPK_CHECK_ARG(w && a && dy && dy1 && g && ws, "ffn_bwd: null pointer");
+  return ffn_bwd_impl(s, w, a, dy, dy1, g, ws, p_hidden, drop, layer_id, S(stream));
+}
+
+int vlpk_mha_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits, int mask_rows,
+                 const VlpkLayerActs* a, const void* dy1, void* dx, const VlpkLayerGrads* g, const VlpkBwdScratch* ws, float p_attn,
+                 float p_hidden, const VlpkDropout* drop, uint64_t layer_id, void* stream) {
+  VLPK_TRY(check_shape(s));
+  VLPK_CHECK_ARG(w && x && mask_bits && a && dy1 && dx && g && ws, "mha_bwd: null pointer");
+  return mha_bwd_impl(s, w, x, mask_bits, mask_rows, a, dy1, dx, g, ws, p_attn, p_hidden, drop, layer_id, S(stream));
+}
+
+int vlpk_mha_incr_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* mask_bits,
+                      int mask_rows, VlpkLayerActs* a, uint64_t layer_id, void* stream) {
+  VLPK_TRY(check_shape(s));
+  VLPK_CHECK_ARG(w && x && x_kv && x_kv != x && mask_bits && a, "mha_incr_fwd: needs x, x_kv (= cat(history, x)), mask and acts");
+  return mha_fwd_impl(s, w, x, x_kv, mask_bits, mask_rows, a, 0.f, 0.f, nullptr, layer_id, S(stream));
+}
+
+int vlpk_workspace_bytes(const VlpkShape* s, size_t* out3) {
+  VLPK_TRY(check_shape(s));
+  VLPK_CHECK_ARG(out3 != nullptr, "workspace_bytes: null output");
+  const size_t H = s->H, I = s->I, Mq = static_cast<size_t>(s->B) * s->Lq, Mkv = static_cast<size_t>(s->B) * s->Lkv;
+  const size_t kv = (s->Lkv != s->Lq) ? Mkv * 2 * H : 0;
+  out3[0] = 2 * (Mq * (3 * H + 5 * H + 2 * I) + kv) + 4 * (static_cast<size_t>(s->B) * s->heads * s->Lq + 4 * Mq);
+  out3[1] = 2 * (Mq * (7 * H + I + 3 * H));
+  out3[2] = 4 * (3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H);
+  return 0;
 }
 
 int vlpk_encoder_fwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w, const void* x, const uint32_t* mask_bits, int mask_rows,
