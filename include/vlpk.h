@@ -193,6 +193,34 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
                      int mask_rows, const VlpkLayerActs* acts, const void* const* dys, void* dx0, const VlpkLayerGrads* grads,
                      const VlpkBwdScratch* ws, float p_attn, float p_hidden, const VlpkDropout* drop, void* stream);
 
+/* ---- optimizer ----------------------------------------------------------------------------------------
+ * One parameter tensor of a BertAdam step.  64 bytes; the table is read by the kernels from DEVICE memory. */
+typedef struct VlpkAdamTensor {
+  void* param;         /* model parameter, updated in place; bf16 or fp32 */
+  const void* grad;    /* its gradient; bf16 or fp32; NOT modified (the reference's clip rescales p.grad in place) */
+  float* master;       /* fp32 master copy, required when param is bf16 (param = bf16(master)); NULL when param is fp32 */
+  float* m;            /* fp32 first moment  (state['next_m']) */
+  float* v;            /* fp32 second moment (state['next_v']) */
+  int64_t n;           /* elements (> 0) */
+  float weight_decay;  /* this tensor's group['weight_decay'] (0 for bias / LayerNorm.*, run_img2txt_dist.py:394-401) */
+  int32_t param_dtype; /* VLPK_BF16 / VLPK_F32 */
+  int32_t grad_dtype;
+  int32_t reserved;
+} VlpkAdamTensor;
+
+/* Elements of one tensor per work item: chunk_prefix[t+1] - chunk_prefix[t] == ceil(tensors[t].n / vlpk_bertadam_chunk()). */
+int vlpk_bertadam_chunk(void);
+/* BertAdam.step (pytorch_pretrained_bert/optimization.py:112-182) for n_tensors parameters at once:
+ *   per tensor  g *= min(1, max_grad_norm / (||g||_2 + 1e-6))   (clip_grad_norm_ of that single tensor, :145-146; skipped if <= 0)
+ *               m = b1 m + (1-b1) g ;  v = b2 v + (1-b2) g g ;  u = m / (sqrt(v) + eps) + weight_decay p ;  p -= lr_scheduled u
+ * No bias correction (:176-179).  lr_scheduled = lr * schedule(step / t_total, warmup) is evaluated by the caller (:165-170).
+ * tensors_dev / chunk_prefix_dev: device copies of tensors_host / chunk_prefix_host ([n_tensors] / [n_tensors+1] exclusive prefix
+ * of chunk counts); the host copies are used for validation only.  sqnorm_dev: [n_tensors] fp32 scratch.  Two launches, no host
+ * synchronisation. */
+int vlpk_bertadam_step(const VlpkAdamTensor* tensors_host, const VlpkAdamTensor* tensors_dev, const int32_t* chunk_prefix_host,
+                       const int32_t* chunk_prefix_dev, int n_tensors, float* sqnorm_dev, double lr_scheduled, double b1, double b2,
+                       double eps, double max_grad_norm, void* stream);
+
 /* Launch accounting.  vlpk_launch_count: kernels launched by this library in this process.  With profiling enabled every
  * launch is bracketed by CUDA events on its stream; vlpk_profile_get sums device time (ms), algorithmic work (FLOPs for the
  * tensor-core kernels, HBM bytes for the bandwidth kernels) and launches of one kernel family since the last reset.

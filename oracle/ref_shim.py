@@ -36,6 +36,18 @@ def import_reference_modeling():
     return m
 
 
+def import_reference_optimization():
+    """pytorch_pretrained_bert/optimization.py (BertAdam).  Its only obstacle on a modern stack is `from torch._six import
+    container_abcs` (:27, unused by BertAdam itself): a stub module provides the name."""
+    import collections.abc
+    import_reference_modeling()          # registers the package object
+    six = types.ModuleType("torch._six")
+    six.container_abcs = collections.abc
+    sys.modules.setdefault("torch._six", six)
+    import pytorch_pretrained_bert.optimization as o  # noqa: E402
+    return o
+
+
 def build_reference_model(dims, state_dict, tasks="img2txt", decoder=False, **decoder_kw):
     """Instantiate the reference's BertForPreTrainingLossMask / BertForSeq2SeqDecoder (enable_butd=True) and
     load `state_dict`.  modeling.py:1008-1014 reads detectron_weights/fc7_{w,b}.pkl from the CWD at

@@ -71,13 +71,18 @@ def test_library_exports_every_declared_symbol():
 def test_install_shadows_reference_import_path():
     import sys
     from vlp_b200 import install
-    saved = {k: sys.modules.get(k) for k in ("pytorch_pretrained_bert", "pytorch_pretrained_bert.modeling")}
+    saved = {k: sys.modules.get(k) for k in ("pytorch_pretrained_bert", "pytorch_pretrained_bert.modeling", "pytorch_pretrained_bert.optimization")}
     try:
         for k in saved:
             sys.modules.pop(k, None)
         install.install()
         from pytorch_pretrained_bert.modeling import BertForPreTrainingLossMask, BertForSeq2SeqDecoder  # noqa: F401
         assert BertForPreTrainingLossMask is vm.BertForPreTrainingLossMask
+        assert "pytorch_pretrained_bert.optimization" not in sys.modules          # the optimizer is opt-in
+        install.install(optimizer=True)
+        from pytorch_pretrained_bert.optimization import BertAdam, warmup_linear  # noqa: F401  (run_img2txt_dist.py:25)
+        from vlp_b200 import optimization as vo
+        assert BertAdam is vo.BertAdam and warmup_linear(0.05, 0.1) == 0.5
     finally:
         for k, v in saved.items():
             if v is None:
@@ -246,3 +251,73 @@ def test_greedy_decode_marshalling_dry_run():
     assert ids.shape == (B, steps)
     assert calls.count("vlpk_layer_fwd") + calls.count("vlpk_encoder_fwd") * cfg.num_hidden_layers >= steps * cfg.num_hidden_layers
     assert calls.count("vlpk_embed_fwd") == steps and "vlpk_encoder_bwd" not in calls
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# BertAdam: host side
+# ---------------------------------------------------------------------------------------------------------------------------
+def test_bertadam_surface_matches_reference_contract():
+    """Constructor validation, schedules, state keys and get_lr() of vlp_b200.optimization.BertAdam follow
+    pytorch_pretrained_bert/optimization.py:32-110; the step itself is marshalled under the dry-run (nothing computed)."""
+    import pytest
+    from tools import abi_cases
+    from vlp_b200 import optimization as opt_mod
+    assert set(opt_mod.SCHEDULES) == {"warmup_cosine", "warmup_constant", "warmup_linear"}
+    assert opt_mod.warmup_linear(0.05, 0.1) == 0.5 and opt_mod.warmup_linear(2.0, 0.1) == 0 and opt_mod.warmup_constant(0.5, 0.1) == 1.0
+    w = torch.nn.Parameter(torch.randn(5, 3).bfloat16())
+    b = torch.nn.Parameter(torch.randn(7))
+    unused = torch.nn.Parameter(torch.randn(2))
+    for bad in (dict(lr=-1.0), dict(lr=1e-3, schedule="nope"), dict(lr=1e-3, warmup=1.5), dict(lr=1e-3, b1=1.0), dict(lr=1e-3, b2=-0.1),
+                dict(lr=1e-3, e=-1.0)):
+        with pytest.raises(ValueError):
+            opt_mod.BertAdam([w], **bad)
+    opt = opt_mod.BertAdam([{"params": [w], "weight_decay": 0.01}, {"params": [b, unused], "weight_decay": 0.0}], lr=1e-3, warmup=0.1, t_total=100)
+    assert opt.get_lr() == [0]                                  # no state yet (optimization.py:94-95)
+    w.grad, b.grad = torch.randn(5, 3).bfloat16(), torch.randn(7)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()                                              # no CPU path
+    with abi_cases.dry_run() as calls:
+        opt.step()
+        opt.step()
+    assert calls == ["vlpk_bertadam_step"] * 2                  # both weight-decay groups share one launch pair
+    assert set(opt.state[w]) == {"step", "next_m", "next_v", "master"} and set(opt.state[b]) == {"step", "next_m", "next_v"}
+    assert opt.state[w]["next_m"].dtype == torch.float32 and opt.state[w]["master"].dtype == torch.float32
+    assert opt.state[w]["step"] == 2 and len(opt.state[unused]) == 0     # parameters without a gradient are skipped (:128-129)
+    # schedule evaluated at the pre-increment step (:164-174): after 2 steps get_lr reports step 2
+    assert opt.get_lr() == [0]                                  # reference quirk kept: ANY stateless parameter short-circuits (:94-95)
+    opt.param_groups[1]["params"] = [b]
+    assert len(opt.get_lr()) == 2 and all(abs(l - 1e-3 * opt_mod.warmup_linear(2 / 100, 0.1)) < 1e-15 for l in opt.get_lr())
+    opt.param_groups[1]["params"] = [b, unused]
+    sd = opt.state_dict()
+    opt2 = opt_mod.BertAdam([{"params": [w], "weight_decay": 0.01}, {"params": [b, unused], "weight_decay": 0.0}], lr=1e-3, warmup=0.1, t_total=100)
+    opt2.load_state_dict(sd)
+    assert opt2.state[w]["step"] == 2 and torch.equal(opt2.state[w]["master"], opt.state[w]["master"])
+
+
+def test_bertadam_host_validation_in_the_library():
+    """vlpk_bertadam_step validates the HOST copy of the descriptor table before anything is launched (rc < 0)."""
+    import ctypes as C
+    import numpy as np
+    from vlp_b200 import optimization as opt_mod
+    lib = _lib.lib()
+    chunk = lib.vlpk_bertadam_chunk()
+    assert chunk == 4096
+    tab = np.zeros(2, dtype=opt_mod._TENSOR_DTYPE)
+    tab[0] = (64, 128, 0, 192, 256, 5000, 0.01, 1, 1, 0)
+    tab[1] = (64, 128, 320, 192, 256, 10, 0.0, 0, 0, 0)
+    prefix = np.array([0, 2, 3], dtype=np.int32)
+
+    def call(t, pf, n=2, b1=0.9):
+        return lib.vlpk_bertadam_step(t.ctypes.data, 4096, pf.ctypes.data, 8192, n, 12288, 1e-3, b1, 0.999, 1e-6, 1.0, None)
+
+    bad = tab.copy(); bad["n"][1] = 0
+    assert call(bad, prefix) < 0 and b"empty" in lib.vlpk_last_error()
+    bad = tab.copy(); bad["master"][1] = 0
+    assert call(bad, prefix) < 0 and b"master" in lib.vlpk_last_error()
+    bad = tab.copy(); bad["grad_dtype"][0] = 2
+    assert call(bad, prefix) < 0 and b"bf16 or fp32" in lib.vlpk_last_error()
+    bad = tab.copy(); bad["m"][0] = 0
+    assert call(bad, prefix) < 0 and b"null pointer" in lib.vlpk_last_error()
+    assert call(tab, np.array([0, 1, 2], dtype=np.int32)) < 0 and b"chunk prefix" in lib.vlpk_last_error()
+    assert call(tab, prefix, b1=1.0) < 0 and b"out of range" in lib.vlpk_last_error()
+    assert call(tab, prefix, n=0) < 0

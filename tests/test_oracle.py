@@ -93,3 +93,53 @@ def test_oracle_matches_live_reference_when_present():
                     vis_masked_pos=batch["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
         got = O.pretraining_loss(sd, dims, batch)
     assert abs(float(got[0]) - float(ref[0])) < 1e-5
+
+
+def _run_bertadam_oracle():
+    from oracle import bertadam_oracle as bo
+    params, wds, grads = bo.case()
+    ps = [p.clone() for p in params]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    out = []
+    for t in range(bo.CASE_STEPS):
+        gs = [g.clone() for g in grads[t]]
+        lrs = [bo.step(p, g, m, v, t, weight_decay=wd, **bo.CASE_HYPER) for p, g, m, v, wd in zip(ps, gs, ms, vs, wds)]
+        out.append({"p": [p.clone() for p in ps], "m": [m.clone() for m in ms], "v": [v.clone() for v in vs], "grad_after": gs, "lr": lrs})
+    return out
+
+
+def test_bertadam_oracle_matches_reference_golden(golden_dir):
+    """oracle/bertadam_oracle.py vs the reference's own BertAdam (optimization.py:112-182) — parameters, both moments, the
+    in-place clipped gradients and the schedule, three steps, eight tensors straddling the clip threshold."""
+    from oracle import bertadam_oracle as bo
+    gold = torch.load(os.path.join(golden_dir, "bertadam.pt"))
+    mine = _run_bertadam_oracle()
+    assert len(gold["steps"]) == bo.CASE_STEPS
+    for t, (a, b) in enumerate(zip(mine, gold["steps"])):
+        for key in ("p", "m", "v", "grad_after"):
+            for i, (x, y) in enumerate(zip(a[key], b[key])):
+                # sums of opposite-signed terms can cancel, so the bound is a few ulp of the tensor's scale, not of each element
+                # (the 1-ulp source: modern torch evaluates the clip coefficient in fp32, this restatement — like torch 1.1 — in double)
+                err, scale = float((x - y).abs().max()), float(y.abs().max())
+                assert err <= 1e-6 * scale, (t, key, i, err, scale)
+    # schedule: get_lr() before step t reports lr * schedule((t)/t_total) for t >= 1 ([0] before any state exists)
+    h = bo.CASE_HYPER
+    assert gold["steps"][0]["get_lr_before"] == [0]
+    for t in (1, 2):
+        ref_lrs = gold["steps"][t]["get_lr_before"]
+        assert all(abs(l - bo.lr_at(t, h["lr"], h["warmup"], h["t_total"], h["schedule"])) < 1e-12 for l in ref_lrs)
+    # clipping really happened for some tensors and not for others
+    _, _, grads = bo.case()
+    scaled = [not torch.equal(g0, g1) for g0, g1 in zip(grads[0], gold["steps"][0]["grad_after"])]
+    assert any(scaled) and not all(scaled)
+
+
+def test_bertadam_schedules():
+    from oracle import bertadam_oracle as bo
+    assert bo.schedule_value("warmup_linear", 0.05, 0.1) == 0.5
+    assert abs(bo.schedule_value("warmup_linear", 0.55, 0.1) - 0.5) < 1e-12
+    assert bo.schedule_value("warmup_linear", 1.5, 0.1) == 0
+    assert bo.schedule_value("warmup_constant", 0.5, 0.1) == 1.0
+    assert abs(bo.schedule_value("warmup_cosine", 0.5, 0.1) - 0.5) < 1e-12
+    assert bo.lr_at(7, 1e-3) == 1e-3

@@ -46,6 +46,11 @@ class VlpkBwdScratch(C.Structure):
     _fields_ = [(n, c_void_p) for n in SCRATCH_FIELDS]
 
 
+class VlpkAdamTensor(C.Structure):
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("master", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_i64),
+                ("weight_decay", c_float), ("param_dtype", C.c_int32), ("grad_dtype", C.c_int32), ("reserved", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/vlpk.h one to one
 _P = c_void_p
 _SIGS = {
@@ -89,6 +94,8 @@ _SIGS = {
     "vlpk_encoder_bwd": (c_int, [C.POINTER(VlpkShape), c_int, C.POINTER(VlpkLayerWeights), _P, _P, c_int,
                                  C.POINTER(VlpkLayerActs), C.POINTER(c_void_p), _P, C.POINTER(VlpkLayerGrads),
                                  C.POINTER(VlpkBwdScratch), c_float, c_float, C.POINTER(VlpkDropout), _P]),
+    "vlpk_bertadam_chunk": (c_int, []),
+    "vlpk_bertadam_step": (c_int, [_P, _P, _P, _P, c_int, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P]),
     "vlpk_profile_enable": (None, [c_int]),
     "vlpk_profile_reset": (None, []),
     "vlpk_profile_get": (c_int, [c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(c_i64)]),

@@ -9,6 +9,7 @@
 #include "attn.cuh"
 #include "gemm.cuh"
 #include "host.cuh"
+#include "optim.cuh"
 #include "rowops.cuh"
 
 using namespace vlpk;
@@ -518,6 +519,21 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
     cur_dy = out;
   }
   return 0;
+}
+
+int vlpk_bertadam_chunk(void) { return ADAM_CHUNK; }
+
+int vlpk_bertadam_step(const VlpkAdamTensor* tensors_host, const VlpkAdamTensor* tensors_dev, const int32_t* chunk_prefix_host,
+                       const int32_t* chunk_prefix_dev, int n_tensors, float* sqnorm_dev, double lr_scheduled, double b1, double b2,
+                       double eps, double max_grad_norm, void* stream) {
+  VLPK_CHECK_ARG(b1 >= 0.0 && b1 < 1.0 && b2 >= 0.0 && b2 < 1.0 && eps >= 0.0, "bertadam: b1=%g b2=%g eps=%g out of range", b1, b2, eps);
+  AdamHyper h;
+  h.lr = static_cast<float>(lr_scheduled);
+  h.b1 = static_cast<float>(b1); h.omb1 = static_cast<float>(1.0 - b1);
+  h.b2 = static_cast<float>(b2); h.omb2 = static_cast<float>(1.0 - b2);
+  h.eps = static_cast<float>(eps);
+  h.max_grad_norm = static_cast<float>(max_grad_norm);
+  return launch_bertadam(tensors_host, tensors_dev, chunk_prefix_host, chunk_prefix_dev, n_tensors, sqnorm_dev, h, S(stream));
 }
 
 void vlpk_profile_enable(int on) { prof_enable(on != 0); }

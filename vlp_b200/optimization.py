@@ -1,0 +1,153 @@
+"""BertAdam on B200 — same constructor, param-group keys, state keys and schedule functions as the reference's
+pytorch_pretrained_bert/optimization.py:32-182 (imported by vlp/run_img2txt_dist.py:25, built at :422-426), with `step()`
+executed by two launches of libvlpk.so (`vlpk_bertadam_step`, csrc/optim.cu) over ALL parameters instead of the reference's
+Python loop of ~400 tensors x (norm + host read-back + 6 elementwise kernels).
+
+Differences a caller can observe, all deliberate:
+  * bf16 parameters are supported: state['master'] holds an fp32 copy that carries the arithmetic (what the reference's --fp16
+    branch delegates to apex FP16_Optimizer, run_img2txt_dist.py:403-420); moments are always fp32.  fp32 parameters are
+    updated exactly like the reference (no master copy).
+  * gradient clipping does not rescale p.grad in place (the clip factor is applied inside the update kernel).
+  * CUDA only — there is no CPU path; a parameter that lives on the CPU raises.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+from torch.optim import Optimizer
+from torch.optim.optimizer import required
+
+from . import _lib as L
+from . import ops
+
+
+def warmup_cosine(x, warmup=0.002):
+    if x < warmup:
+        return x / warmup
+    return 0.5 * (1.0 + math.cos(math.pi * x))
+
+
+def warmup_constant(x, warmup=0.002):
+    if x < warmup:
+        return x / warmup
+    return 1.0
+
+
+def warmup_linear(x, warmup=0.002):
+    if x < warmup:
+        return x / warmup
+    return max((x - 1.) / (warmup - 1.), 0)
+
+
+SCHEDULES = {'warmup_cosine': warmup_cosine, 'warmup_constant': warmup_constant, 'warmup_linear': warmup_linear}
+
+_TENSOR_DTYPE = np.dtype([("param", "<u8"), ("grad", "<u8"), ("master", "<u8"), ("m", "<u8"), ("v", "<u8"), ("n", "<i8"),
+                          ("weight_decay", "<f4"), ("param_dtype", "<i4"), ("grad_dtype", "<i4"), ("reserved", "<i4")])
+assert _TENSOR_DTYPE.itemsize == C.sizeof(L.VlpkAdamTensor) == 64
+_DT = {torch.bfloat16: 0, torch.float32: 1}     # VLPK_BF16 / VLPK_F32
+
+
+class BertAdam(Optimizer):
+    """BERT version of Adam with decoupled weight decay, per-tensor gradient clipping and no bias correction.
+    Params (optimization.py:58-71): lr; warmup: portion of t_total, -1 = none; t_total: total steps, -1 = constant lr;
+    schedule; b1; b2; e; weight_decay; max_grad_norm (-1 = no clipping)."""
+
+    def __init__(self, params, lr=required, warmup=-1, t_total=-1, schedule='warmup_linear', b1=0.9, b2=0.999, e=1e-6, weight_decay=0.01,
+                 max_grad_norm=1.0):
+        if lr is not required and lr < 0.0:
+            raise ValueError("Invalid learning rate: {} - should be >= 0.0".format(lr))
+        if schedule not in SCHEDULES:
+            raise ValueError("Invalid schedule parameter: {}".format(schedule))
+        if not 0.0 <= warmup < 1.0 and not warmup == -1:
+            raise ValueError("Invalid warmup: {} - should be in [0.0, 1.0[ or -1".format(warmup))
+        if not 0.0 <= b1 < 1.0:
+            raise ValueError("Invalid b1 parameter: {} - should be in [0.0, 1.0[".format(b1))
+        if not 0.0 <= b2 < 1.0:
+            raise ValueError("Invalid b2 parameter: {} - should be in [0.0, 1.0[".format(b2))
+        if not e >= 0.0:
+            raise ValueError("Invalid epsilon value: {} - should be >= 0.0".format(e))
+        defaults = dict(lr=lr, schedule=schedule, warmup=warmup, t_total=t_total, b1=b1, b2=b2, e=e, weight_decay=weight_decay,
+                        max_grad_norm=max_grad_norm)
+        super(BertAdam, self).__init__(params, defaults)
+        self._keep = None     # device tables of the last step (kept alive until the next one)
+
+    @staticmethod
+    def _scheduled_lr(group, step):
+        if group['t_total'] != -1:
+            return group['lr'] * SCHEDULES[group['schedule']](step / group['t_total'], group['warmup'])
+        return group['lr']
+
+    def get_lr(self):
+        lr = []
+        for group in self.param_groups:
+            for p in group['params']:
+                state = self.state[p]
+                if len(state) == 0:
+                    return [0]
+                lr.append(self._scheduled_lr(group, state['step']))
+        return lr
+
+    def _init_state(self, p):
+        state = self.state[p]
+        if len(state) == 0:
+            state['step'] = 0
+            state['next_m'] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+            state['next_v'] = torch.zeros(p.shape, dtype=torch.float32, device=p.device)
+        if p.dtype == torch.bfloat16 and 'master' not in state:
+            state['master'] = p.detach().float().contiguous()
+        return state
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        # One launch pair per distinct (device, scheduled lr, b1, b2, e, max_grad_norm); in practice a single one:
+        # the two weight-decay groups of run_img2txt_dist.py:394-401 differ only in the per-tensor weight_decay field.
+        buckets = {}
+        for group in self.param_groups:
+            for p in group['params']:
+                if p.grad is None:
+                    continue
+                if p.grad.is_sparse:
+                    raise RuntimeError('Adam does not support sparse gradients, please consider SparseAdam instead')
+                if p.dtype not in _DT or p.grad.dtype not in _DT:
+                    raise RuntimeError(f"vlp_b200 BertAdam: parameters / gradients must be bf16 or fp32, got {p.dtype} / {p.grad.dtype}")
+                ops._require_cuda(p, "BertAdam parameters")
+                if not p.is_contiguous():
+                    raise RuntimeError("vlp_b200 BertAdam: parameters must be contiguous")
+                if p.numel() == 0:
+                    continue
+                state = self._init_state(p)
+                key = (p.device, self._scheduled_lr(group, state['step']), group['b1'], group['b2'], group['e'], group['max_grad_norm'])
+                buckets.setdefault(key, []).append((p, state, float(group['weight_decay'])))
+        keep = []
+        for (device, lr_s, b1, b2, e, max_norm), items in buckets.items():
+            keep.append(self._launch(device, items, lr_s, b1, b2, e, max_norm))
+            for _, state, _ in items:
+                state['step'] += 1
+        self._keep = keep
+        return loss
+
+    @staticmethod
+    def _launch(device, items, lr_s, b1, b2, e, max_norm):
+        n = len(items)
+        chunk = L.lib().vlpk_bertadam_chunk()
+        tab = np.zeros(n, dtype=_TENSOR_DTYPE)
+        grads = []
+        for i, (p, state, wd) in enumerate(items):
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            grads.append(g)
+            master = state.get('master')
+            tab[i] = (p.data_ptr(), g.data_ptr(), 0 if master is None else master.data_ptr(), state['next_m'].data_ptr(),
+                      state['next_v'].data_ptr(), p.numel(), wd, _DT[p.dtype], _DT[g.dtype], 0)
+        prefix = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum((tab["n"] + chunk - 1) // chunk, out=prefix[1:])
+        tab_dev = torch.from_numpy(tab.view(np.uint8)).to(device, non_blocking=True)
+        prefix_dev = torch.from_numpy(prefix).to(device, non_blocking=True)
+        sqnorm = torch.empty(n, dtype=torch.float32, device=device)
+        L.call("vlpk_bertadam_step", tab.ctypes.data, tab_dev.data_ptr(), prefix.ctypes.data, prefix_dev.data_ptr(), n, sqnorm.data_ptr(),
+               float(lr_s), float(b1), float(b2), float(e), float(max_norm), L.stream())
+        return tab_dev, prefix_dev, sqnorm, grads
