@@ -193,6 +193,19 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
                      int mask_rows, const VlpkLayerActs* acts, const void* const* dys, void* dx0, const VlpkLayerGrads* grads,
                      const VlpkBwdScratch* ws, float p_attn, float p_hidden, const VlpkDropout* drop, void* stream);
 
+/* ---- masked-LM head tail -------------------------------------------------------------------------------
+ * cls.predictions.decoder (weight tied to the word embeddings [V,H], output-only bias; modeling.py:465-482) + the per-position
+ * cross-entropy of crit_mask_lm (modeling.py:1108-1109), without fp32 logits.  Vp = V rounded up to a multiple of 8.
+ *   h [R,H] bf16 (output of cls.predictions.transform), w [V,H] bf16 read in place, bias_pad [Vp] bf16 (zero padded),
+ *   labels [R] int64 (outside [0,V): ignored position, loss 0 / no gradient, like ignore_index),
+ *   logits [R,Vp] bf16 (out), lse [R] fp32 (out), loss [R] fp32 (out). */
+int vlpk_decoder_ce_fwd(int R, int V, int H, const void* h, const void* w, const void* bias_pad, const int64_t* labels, void* logits,
+                        float* lse, float* loss, void* stream);
+/* Backward: dloss [R] fp32 -> dlogits [R,Vp] bf16 (scratch/out), dh [R,H] fp32 (ZEROED by the caller; split-K reduce-add target),
+ * dw [V,H] bf16 (overwritten), dbias [Vp] fp32 (ZEROED by the caller). */
+int vlpk_decoder_ce_bwd(int R, int V, int H, const void* h, const void* w, const int64_t* labels, const void* logits, const float* lse,
+                        const float* dloss, void* dlogits, float* dh, void* dw, float* dbias, void* stream);
+
 /* ---- optimizer ----------------------------------------------------------------------------------------
  * One parameter tensor of a BertAdam step.  64 bytes; the table is read by the kernels from DEVICE memory. */
 typedef struct VlpkAdamTensor {

@@ -164,6 +164,11 @@ def test_gemm_plan_for_the_hot_shapes():
         tiles = ((n + 128 * cg - 1) // (128 * cg)) * ((k + bn - 1) // bn) * s
         assert cg == 2 and s >= 2 and 60 <= tiles <= 2 * 74
         assert (123 + s - 1) // s >= 8                                         # at least 8 k-blocks per work item
+    # masked-LM head tail (csrc/head.cu): logits, split-K contraction over the vocabulary, direct bf16 weight gradient
+    assert _plan(192, 29000, 768) == (256, 2, 1)
+    bn, cg, s = _plan(192, 768, 29000, b_mn=1, epi=6, splits=0)
+    assert cg == 2 and 60 <= 3 * s <= 74
+    assert _plan(28996, 768, 192, a_mn=1, b_mn=1, epi=0)[2] == 1
     # MN-major B never gets a tile whose per-CTA share is not whole 64-wide boxes; forced shapes are honoured
     assert _plan(M, 768, 768, b_mn=1)[0] in (128, 256)
     assert _plan(M, 768, 768, bn=128)[0] == 128
@@ -321,3 +326,25 @@ def test_bertadam_host_validation_in_the_library():
     assert call(tab, np.array([0, 1, 2], dtype=np.int32)) < 0 and b"chunk prefix" in lib.vlpk_last_error()
     assert call(tab, prefix, b1=1.0) < 0 and b"out of range" in lib.vlpk_last_error()
     assert call(tab, prefix, n=0) < 0
+
+
+def test_fused_mlm_head_marshalling_dry_run():
+    """Opt-in fused decoder + cross-entropy path (VLP_FUSED_HEAD=1 / model.fused_mlm_head): call sequence and gradient plumbing on
+    CPU (values meaningless) — the tied decoder weight receives a gradient from both the head and the embedding lookup."""
+    from tools import abi_cases
+    d, cfg = _tiny_config()
+    model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions).bfloat16().train()
+    assert model.fused_mlm_head is False                        # default path unchanged
+    model.fused_mlm_head = True
+    b = synth.make_batch(d, 2, seed=1)
+    with abi_cases.dry_run() as calls:
+        out = model(b["img"].bfloat16(), b["vis_pe"].bfloat16(), b["input_ids"], b["segment_ids"], b["input_mask"], b["masked_ids"], None,
+                    b["is_next"], masked_pos=b["masked_pos"], masked_weights=b["masked_weights"], task_idx=b["task_idx"],
+                    vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
+        sum(l.float().sum() for l in out).backward()
+    assert calls == ["vlpk_linear_fwd"] * 3 + ["vlpk_embed_fwd", "vlpk_mask_pack", "vlpk_encoder_fwd", "vlpk_decoder_ce_fwd", "vlpk_decoder_ce_bwd",
+                     "vlpk_encoder_bwd", "vlpk_f32_to_bf16", "vlpk_embed_bwd"] + ["vlpk_linear_bwd"] * 3
+    assert model.last_prediction_scores.shape == (2, b["masked_pos"].shape[1], d.vocab)
+    for n in ("cls.predictions.bias", "cls.predictions.transform.dense.weight", "bert.embeddings.word_embeddings.weight"):
+        p = dict(model.named_parameters())[n]
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == p.dtype, n

@@ -1,0 +1,69 @@
+"""GPU parity of the opt-in fused masked-LM head tail (csrc/head.cu, vlpk_decoder_ce_fwd/bwd): against plain
+fp32 PyTorch math of the same op, and — through the model — against the default (torch) head on identical weights and inputs.
+
+Tolerance: logits are bf16 on both paths (|logit| <= ~4 -> one bf16 ulp = 1.6e-2), so per-position losses agree to 3e-2 absolute;
+gradients to rel-L2 2e-2 (bf16 dlogits)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tools.gating import unverified_on_gpu
+from vlp_b200 import ops, synth
+from vlp_b200 import vlp_modules as vm
+
+pytestmark = [pytest.mark.gpu, unverified_on_gpu]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("R,V,H", [(6, 1003, 128), (192, 28996, 768)])
+def test_decoder_ce_matches_fp32_torch(R, V, H):
+    gen = torch.Generator().manual_seed(3)
+    h = (torch.randn(R, H, generator=gen)).cuda().bfloat16().requires_grad_(True)
+    w = (torch.randn(V, H, generator=gen) * 0.05).cuda().bfloat16().requires_grad_(True)
+    bias = (torch.randn(V, generator=gen) * 0.1).cuda().bfloat16().requires_grad_(True)
+    labels = torch.randint(0, V, (R,), generator=gen).cuda()
+    labels[1] = -100                                              # ignored position
+    wts = torch.rand(R, generator=gen).cuda()
+    loss, scores = ops.DecoderCEFn.apply(h, w, bias, labels)
+    (loss * wts).sum().backward()
+    got = (h.grad.clone(), w.grad.clone(), bias.grad.clone())
+    h32, w32, b32 = (t.detach().float().requires_grad_(True) for t in (h, w, bias))
+    logits = h32 @ w32.t() + b32
+    ref = F.cross_entropy(logits, labels, reduction="none", ignore_index=-100)
+    (ref * wts).sum().backward()
+    torch.cuda.synchronize()
+    assert scores.shape == (R, V) and rel(scores.float(), logits) < 1e-2
+    assert float((loss - ref).abs().max()) < 3e-2 and float(loss[1]) == 0.0
+    assert rel(got[0], h32.grad) < 2e-2 and rel(got[1], w32.grad) < 2e-2 and rel(got[2], b32.grad) < 2e-2
+    assert float(got[0][1].abs().max()) == 0.0                    # no gradient from the ignored position
+
+
+def test_model_with_fused_head_matches_default_head():
+    d = synth.SMALL_L123
+    cfg = vm.BertConfig(d.vocab, hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads, intermediate_size=d.inter,
+                        type_vocab_size=d.type_vocab, max_position_embeddings=d.max_pos, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd = synth.make_state_dict(d, 0)
+    batch = {k: v.cuda() for k, v in synth.make_batch(d, 4, seed=11, mode="s2s", ragged=True).items()}
+    outs = []
+    for fused in (False, True):
+        model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions)
+        model.load_state_dict(sd)
+        model = model.cuda().bfloat16().eval()
+        model.fused_mlm_head = fused
+        losses = model(batch["img"].bfloat16(), batch["vis_pe"].bfloat16(), batch["input_ids"], batch["segment_ids"], batch["input_mask"],
+                       batch["masked_ids"], None, batch["is_next"], masked_pos=batch["masked_pos"], masked_weights=batch["masked_weights"],
+                       task_idx=batch["task_idx"], vis_masked_pos=batch["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
+        sum(l.float().sum() for l in losses).backward()
+        torch.cuda.synchronize()
+        outs.append((float(losses[0]), {n: p.grad.detach().float().cpu() for n, p in model.named_parameters() if p.grad is not None},
+                     model.last_prediction_scores.detach().float().cpu()))
+    (l0, g0, s0), (l1, g1, s1) = outs
+    assert abs(l0 - l1) < 2e-2 and rel(s1, s0) < 1e-2
+    assert set(g0) == set(g1)
+    for n in g0:
+        if float(g0[n].norm()) > 0:
+            assert rel(g1[n], g0[n]) < 5e-2, n

@@ -6,8 +6,11 @@
 // host call — the reference spends ~60 Python module calls per layer.
 #include "../../include/vlpk.h"
 
+#include <cstdlib>
+
 #include "attn.cuh"
 #include "gemm.cuh"
+#include "head.cuh"
 #include "host.cuh"
 #include "optim.cuh"
 #include "rowops.cuh"
@@ -77,6 +80,51 @@ int wgrad_linear(int M, int N, int K, const void* dy, int64_t lddy, const void* 
   g.epi = EPI_REDUCE_F32;
   g.splits = 0;  // chosen together with the tile shape by launch_gemm's cost model
   return launch_gemm(g, st);
+}
+
+// ---- experiment (VLPK_WGRAD_STREAM=1, default off): weight-gradient GEMMs of the layer backward on a side stream -------------
+// Inside one layer the wgrad of a Linear and the dgrad of the same Linear only share their INPUT, so they may run concurrently.
+// Both are persistent one-CTA-per-SM kernels: issued on two streams, the CTAs of the second start on the SMs the first kernel's
+// partial last wave leaves idle (93 pair-tiles on 74 CTA pairs for the N = 768 shapes), instead of after its last tile.  Fork /
+// join with events (capturable in a CUDA graph); one process drives one GPU, so a single side stream per process is enough.
+struct WgradSide {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool pending = false;
+};
+
+WgradSide* wgrad_side() {
+  static int enabled = -1;
+  static WgradSide side;
+  if (enabled < 0) {
+    const char* e = getenv("VLPK_WGRAD_STREAM");
+    enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
+    if (enabled && (cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming) != cudaSuccess))
+      enabled = 0;
+  }
+  return enabled ? &side : nullptr;
+}
+
+// wgrad_linear that may run beside the kernels issued on `main` after it; wgrad_join(main) must follow before its inputs are reused.
+int wgrad_overlapped(int M, int N, int K, const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
+                     cudaStream_t main) {
+  WgradSide* sd = wgrad_side();
+  if (sd == nullptr) return wgrad_linear(M, N, K, dy, lddy, x, ldx, dw, lddw, main);
+  VLPK_CUDA(cudaEventRecord(sd->fork, main));
+  VLPK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+  sd->pending = true;
+  return wgrad_linear(M, N, K, dy, lddy, x, ldx, dw, lddw, sd->stream);
+}
+
+int wgrad_join(cudaStream_t main) {
+  WgradSide* sd = wgrad_side();
+  if (sd == nullptr || !sd->pending) return 0;
+  VLPK_CUDA(cudaEventRecord(sd->join, sd->stream));
+  VLPK_CUDA(cudaStreamWaitEvent(main, sd->join, 0));
+  sd->pending = false;
+  return 0;
 }
 
 int mha_fwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* bits, int mask_rows,
@@ -171,11 +219,12 @@ int ffn_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const VlpkLayerA
   VLPK_TRY(launch_ln_res_drop_bwd(l2, st));
   const void* dt2 = hdrop ? ws->dt2 : ws->dz2;
   // ---- output.dense: dW2 += dt2^T hmid ; dU = (dt2 W2) * gelu'(u)   [gelu'(u) was stored by the forward epilogue in acts.u]
-  VLPK_TRY(wgrad_linear(M, H, I, dt2, H, a->hmid, I, g->w2, I, st));
+  VLPK_TRY(wgrad_overlapped(M, H, I, dt2, H, a->hmid, I, g->w2, I, st));
   VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, st, g->b1));  // + db1 = column sums of dU
   // ---- intermediate.dense: dW1 += dU^T y1 ; dy1 = dU W1 + dz2 (residual branch of LN2)
-  VLPK_TRY(wgrad_linear(M, I, H, ws->du, I, a->y1, H, g->w1, H, st));
-  return dgrad_linear(M, I, H, ws->du, I, w->w1, H, dy1, H, EPI_ADD, ws->dz2, H, st);
+  VLPK_TRY(wgrad_overlapped(M, I, H, ws->du, I, a->y1, H, g->w1, H, st));
+  VLPK_TRY(dgrad_linear(M, I, H, ws->du, I, w->w1, H, dy1, H, EPI_ADD, ws->dz2, H, st));
+  return wgrad_join(st);
 }
 
 // Backward of BertAttention.  dy1: gradient of a->y1; dx: receives the gradient of the layer input x (attention branch +
@@ -199,7 +248,7 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   VLPK_TRY(launch_ln_res_drop_bwd(l1, st));
   const void* dt1 = hdrop ? ws->dt1 : ws->dz1;
   // ---- attention.output.dense
-  VLPK_TRY(wgrad_linear(M, H, H, dt1, H, a->ctx, H, g->wo, H, st));
+  VLPK_TRY(wgrad_overlapped(M, H, H, dt1, H, a->ctx, H, g->wo, H, st));
   VLPK_TRY(dgrad_linear(M, H, H, dt1, H, w->wo, H, ws->dctx, H, EPI_STORE, nullptr, 0, st));
   // ---- attention core
   AttnDesc ad;
@@ -214,7 +263,7 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   ad.dbias = g->bqkv;   // d bqkv = column sums of dQ | dK | dV, folded inside the attention backward kernel
   VLPK_TRY(launch_attn_bwd(ad, st));
   // ---- QKV projection: dWqkv += dqkv^T x ; dx = dqkv Wqkv + dz1 (residual branch of LN1)
-  VLPK_TRY(wgrad_linear(M, 3 * H, H, ws->dqkv, 3 * H, x, H, g->wqkv, H, st));
+  VLPK_TRY(wgrad_overlapped(M, 3 * H, H, ws->dqkv, 3 * H, x, H, g->wqkv, H, st));
   GemmDesc d;
   d.M = M; d.N = H; d.K = 3 * H;
   d.A = ws->dqkv; d.lda = 3 * H;
@@ -223,7 +272,8 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   d.D0 = dx; d.ldd0 = H;
   d.epi = EPI_ADD;
   d.aux = static_cast<const bf16*>(ws->dz1); d.ld_aux = H;
-  return launch_gemm(d, st);
+  VLPK_TRY(launch_gemm(d, st));
+  return wgrad_join(st);
 }
 
 int layer_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const uint32_t* bits, int mask_rows,
@@ -519,6 +569,29 @@ int vlpk_encoder_bwd(const VlpkShape* s, int n_layers, const VlpkLayerWeights* w
     cur_dy = out;
   }
   return 0;
+}
+
+int vlpk_decoder_ce_fwd(int R, int V, int H, const void* h, const void* w, const void* bias_pad, const int64_t* labels, void* logits,
+                        float* lse, float* loss, void* stream) {
+  DecoderCeArgs a;
+  a.R = R; a.V = V; a.H = H;
+  a.h = h; a.w = w; a.bias_pad = bias_pad;
+  a.labels = reinterpret_cast<const long long*>(labels);
+  a.logits = logits; a.dlogits = logits;  // (alignment check only)
+  a.lse = lse; a.loss = loss;
+  return launch_decoder_ce_fwd(a, S(stream));
+}
+
+int vlpk_decoder_ce_bwd(int R, int V, int H, const void* h, const void* w, const int64_t* labels, const void* logits, const float* lse,
+                        const float* dloss, void* dlogits, float* dh, void* dw, float* dbias, void* stream) {
+  DecoderCeArgs a;
+  a.R = R; a.V = V; a.H = H;
+  a.h = h; a.w = w;
+  a.labels = reinterpret_cast<const long long*>(labels);
+  a.logits = const_cast<void*>(logits);
+  a.lse = const_cast<float*>(lse);
+  a.dloss = dloss; a.dlogits = dlogits; a.dh = dh; a.dw = dw; a.dbias = dbias;
+  return launch_decoder_ce_bwd(a, S(stream));
 }
 
 int vlpk_bertadam_chunk(void) { return ADAM_CHUNK; }

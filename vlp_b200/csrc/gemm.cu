@@ -545,10 +545,12 @@ static int dispatch(const GemmDesc& g, const GemmTmaps& tm, const GemmArgs& args
       case EPI_ADD: return launch_inst<BN, CG, false, true, EPI_ADD>(tm, args, num_work, s);
       case EPI_MUL: return launch_inst<BN, CG, false, true, EPI_MUL>(tm, args, num_work, s);
       case EPI_DRELU: return launch_inst<BN, CG, false, true, EPI_DRELU>(tm, args, num_work, s);
+      case EPI_REDUCE_F32: return launch_inst<BN, CG, false, true, EPI_REDUCE_F32>(tm, args, num_work, s);  // split-K dgrad (MLM head)
       default: break;
     }
   } else if (g.a_mn && g.b_mn) {
     if (g.epi == EPI_REDUCE_F32) return launch_inst<BN, CG, true, true, EPI_REDUCE_F32>(tm, args, num_work, s);
+    if (g.epi == EPI_STORE) return launch_inst<BN, CG, true, true, EPI_STORE>(tm, args, num_work, s);        // bf16 wgrad, no split-K
   }
   set_error("gemm: unsupported (a_mn=%d, b_mn=%d, epi=%d) combination", (int)g.a_mn, (int)g.b_mn, g.epi);
   return -1;
@@ -630,6 +632,7 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   const int seg_rows = g.nseg > 1 ? g.b_seg_rows : (g.b_mn ? g.K : g.N);
   const bool reduce = (g.epi == EPI_REDUCE_F32);
   VLPK_CHECK_ARG(g.splits <= 1 || reduce, "gemm: split-K needs EPI_REDUCE_F32");
+  VLPK_CHECK_ARG(g.b_rows == 0 || (g.nseg == 1 && g.b_rows <= (g.b_mn ? g.K : g.N)), "gemm: b_rows=%d needs a single B segment", g.b_rows);
 
   // ---- choose tile N, CTA-group size and split-K
   int bn = 128, cg = 1, splits = 1;
@@ -644,10 +647,10 @@ int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
   }
   for (int s = 0; s < g.nseg; ++s) {
     if (!g.b_mn) {
-      const int rows = g.nseg > 1 ? seg_rows : g.N;
+      const int rows = g.nseg > 1 ? seg_rows : (g.b_rows > 0 ? g.b_rows : g.N);
       VLPK_TRY(make_tmap_2d(&tm.b[s], TM_BF16, g.B[s], g.K, rows, g.ldb, BK, bn / cg));
     } else {
-      const int rows = g.nseg > 1 ? seg_rows : g.K;
+      const int rows = g.nseg > 1 ? seg_rows : (g.b_rows > 0 ? g.b_rows : g.K);
       VLPK_TRY(make_tmap_2d(&tm.b[s], TM_BF16, g.B[s], g.N, rows, g.ldb, 64, BK));
     }
   }

@@ -31,6 +31,7 @@ struct GemmDesc {
   const void* B[3] = {nullptr, nullptr, nullptr};
   int64_t ldb = 0;
   int b_seg_rows = 0;
+  int b_rows = 0;  // nseg == 1 only: rows that really exist in B's slow dimension (0 = all N resp. K); the rest is zero-filled by TMA
   const __nv_bfloat16* bias[3] = {nullptr, nullptr, nullptr};  // per N-segment (b_mn=false only)
   void* D0 = nullptr;
   int64_t ldd0 = 0;

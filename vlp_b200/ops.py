@@ -346,3 +346,49 @@ class EmbedFn(torch.autograd.Function):
         out = [None if d_vis is None else d_vis.to(dts[0]), None if d_vis is None else d_vis.to(dts[1]), d_word.to(dts[2]), d_pos.to(dts[3]),
                d_type.to(dts[4]), dg.to(dts[5]), db.to(dts[6])]
         return tuple(out) + (None,) * 7
+
+
+# ------------------------------------------------------------------------------------------------
+# masked-LM head tail: tied decoder + bias + per-position cross-entropy (opt-in)
+# ------------------------------------------------------------------------------------------------
+class DecoderCEFn(torch.autograd.Function):
+    """loss[r] = CE(h[r] W^T + bias, labels[r]) (modeling.py:478-482 + 1108-1109) without fp32 logits; also returns the bf16
+    logits [R,V] (non-differentiable view, kept for `last_prediction_scores`)."""
+
+    @staticmethod
+    def forward(ctx, h, w, bias, labels):
+        _require_cuda(h, "decoder input")
+        R, H = h.shape
+        V = w.shape[0]
+        Vp = (V + 7) // 8 * 8
+        hc, wc = _bf16c(h), _bf16c(w)
+        bias_pad = torch.zeros(Vp, device=h.device, dtype=BF16)
+        bias_pad[:V] = bias
+        labels = labels.contiguous()
+        logits = torch.empty(R, Vp, device=h.device, dtype=BF16)
+        lse = torch.empty(R, device=h.device, dtype=torch.float32)
+        loss = torch.empty(R, device=h.device, dtype=torch.float32)
+        L.call("vlpk_decoder_ce_fwd", R, V, H, hc.data_ptr(), wc.data_ptr(), bias_pad.data_ptr(), labels.data_ptr(), logits.data_ptr(),
+               lse.data_ptr(), loss.data_ptr(), L.stream())
+        ctx.save_for_backward(hc, wc, labels, logits, lse)
+        ctx.meta = (h.dtype, w.dtype, bias.dtype)
+        scores = logits[:, :V]
+        ctx.mark_non_differentiable(scores)
+        return loss, scores
+
+    @staticmethod
+    def backward(ctx, dloss, _dscores):
+        hc, wc, labels, logits, lse = ctx.saved_tensors
+        hdt, wdt, bdt = ctx.meta
+        R, H = hc.shape
+        V = wc.shape[0]
+        Vp = logits.shape[1]
+        dev = hc.device
+        dl = dloss.to(torch.float32).contiguous()
+        dlogits = torch.empty(R, Vp, device=dev, dtype=BF16)
+        dh = torch.zeros(R, H, device=dev, dtype=torch.float32)
+        dw = torch.empty(V, H, device=dev, dtype=BF16)
+        dbias = torch.zeros(Vp, device=dev, dtype=torch.float32)
+        L.call("vlpk_decoder_ce_bwd", R, V, H, hc.data_ptr(), wc.data_ptr(), labels.data_ptr(), logits.data_ptr(), lse.data_ptr(), dl.data_ptr(),
+               dlogits.data_ptr(), dh.data_ptr(), dw.data_ptr(), dbias.data_ptr(), L.stream())
+        return dh.to(hdt), dw.to(wdt), dbias[:V].to(bdt), None

@@ -510,6 +510,7 @@ class BertForPreTrainingLossMask(PreTrainedBertModel, _RegionProjections):
         self._build_region_projections(config, enable_butd)
         self._load_fc7(required=False)
         self.tasks = tasks
+        self.fused_mlm_head = os.environ.get("VLP_FUSED_HEAD", "0") == "1"
         if tasks == "vqa2":
             self.ans_classifier = nn.Sequential(nn.Linear(config.hidden_size, config.hidden_size * 2), nn.ReLU(),
                                                 nn.Linear(config.hidden_size * 2, 3129))
@@ -557,13 +558,21 @@ class BertForPreTrainingLossMask(PreTrainedBertModel, _RegionProjections):
             masked_lm_loss = pooled_output.new(1).fill_(0).float()
         else:
             gathered = torch.gather(sequence_output, 1, masked_pos.unsqueeze(2).expand(-1, -1, sequence_output.size(-1)))
-            prediction_scores_masked, _ = self.cls(gathered, pooled_output, task_idx=task_idx)
-            self.last_prediction_scores = prediction_scores_masked
-            # same per-position CE as crit_mask_lm(scores.transpose(1, 2).float(), labels) (modeling.py:1108-1109), evaluated on the
-            # contiguous [B*P, V] view so that the softmax reduces over the unit-stride dimension
-            V = prediction_scores_masked.size(-1)
-            masked_lm_loss = F.cross_entropy(prediction_scores_masked.reshape(-1, V).float(), masked_lm_labels.reshape(-1),
-                                             reduction="none").view_as(masked_lm_labels)
+            if self.fused_mlm_head:                          # opt-in (VLP_FUSED_HEAD=1): decoder + bias + CE in libvlpk, SURVEY.md §8f-3
+                pred = self.cls.predictions
+                hid = pred.transform(gathered.to(pred.decoder.weight.dtype))
+                loss_flat, scores = ops.DecoderCEFn.apply(hid.reshape(-1, hid.size(-1)), pred.decoder.weight, pred.bias,
+                                                          masked_lm_labels.reshape(-1))
+                self.last_prediction_scores = scores.view(*masked_lm_labels.shape, -1)
+                masked_lm_loss = loss_flat.view_as(masked_lm_labels)
+            else:
+                prediction_scores_masked, _ = self.cls(gathered, pooled_output, task_idx=task_idx)
+                self.last_prediction_scores = prediction_scores_masked
+                # same per-position CE as crit_mask_lm(scores.transpose(1, 2).float(), labels) (modeling.py:1108-1109), evaluated on
+                # the contiguous [B*P, V] view so that the softmax reduces over the unit-stride dimension
+                V = prediction_scores_masked.size(-1)
+                masked_lm_loss = F.cross_entropy(prediction_scores_masked.reshape(-1, V).float(), masked_lm_labels.reshape(-1),
+                                                 reduction="none").view_as(masked_lm_labels)
             masked_lm_loss = loss_mask_and_normalize(masked_lm_loss.float(), masked_weights, drop_worst_ratio)
 
         if mask_image_regions:                               # Selfie-like pretext, modeling.py:1113-1131
