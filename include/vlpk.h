@@ -133,6 +133,15 @@ int vlpk_embed_bwd(int B, int L, int H, int R, int vis_input, const int64_t* ids
                    const void* ln_g, const float* stats, const void* dy, void* dz, float* d_ln_g, float* d_ln_b,
                    const VlpkDropout* drop, uint64_t site, void* stream);
 
+/* Scatter of dz (from vlpk_embed_bwd) into the three embedding tables — autograd backward of the nn.Embedding lookups of
+ * BertEmbeddings (modeling.py:217-241).  Rows 1..R of every sample are region rows (vis_input) and do not read the word /
+ * position tables; every row reads the token-type table.  d_word [V,H] bf16 is overwritten (zero except looked-up rows; duplicates
+ * accumulate in fp32 through word_scratch [V,H] fp32, which may be uninitialised); d_pos [P,H] / d_type [T,H] fp32 are
+ * accumulated into (zero them first); T <= 8. */
+int vlpk_embed_tables_bwd(int B, int L, int H, int R, int vis_input, const int64_t* ids, const int64_t* token_type, const int64_t* pos,
+                          const void* dz, int V, int P, int T, void* d_word, float* word_scratch, float* d_pos, float* d_type,
+                          void* stream);
+
 /* y = LayerNorm(dropout(t) + res) (BertSelfOutput / BertOutput tail, modeling.py:315-316, 355-356; eps 1e-5). */
 int vlpk_ln_res_drop_fwd(int64_t M, int H, const void* t, const void* res, const void* gamma, const void* beta, void* y,
                          float* stats, const VlpkDropout* drop, uint64_t site, void* stream);

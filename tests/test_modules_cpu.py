@@ -348,3 +348,37 @@ def test_fused_mlm_head_marshalling_dry_run():
     for n in ("cls.predictions.bias", "cls.predictions.transform.dense.weight", "bert.embeddings.word_embeddings.weight"):
         p = dict(model.named_parameters())[n]
         assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == p.dtype, n
+
+
+def test_fused_table_grads_marshalling_dry_run(monkeypatch):
+    """Opt-in embedding-table gradient path (VLP_FUSED_TABLE_GRADS=1, csrc/tables.cu) under the CPU dry-run."""
+    from tools import abi_cases
+    from vlp_b200 import ops
+    assert ops.FUSED_TABLE_GRADS is False                       # default path unchanged
+    monkeypatch.setattr(ops, "FUSED_TABLE_GRADS", True)
+    d, cfg = _tiny_config()
+    model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions).bfloat16().train()
+    b = synth.make_batch(d, 2, seed=1)
+    with abi_cases.dry_run() as calls:
+        out = model(b["img"].bfloat16(), b["vis_pe"].bfloat16(), b["input_ids"], b["segment_ids"], b["input_mask"], b["masked_ids"], None,
+                    b["is_next"], masked_pos=b["masked_pos"], masked_weights=b["masked_weights"], task_idx=b["task_idx"],
+                    vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
+        sum(l.float().sum() for l in out).backward()
+    i = calls.index("vlpk_embed_bwd")
+    assert calls[i + 1] == "vlpk_embed_tables_bwd"
+    emb = model.bert.embeddings
+    for p in (emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight):
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == p.dtype
+
+
+def test_embed_tables_bwd_argument_validation():
+    lib = _lib.lib()
+    args = dict(B=2, L=15, H=128, R=4, vis=1, V=100, P=64, T=6)
+
+    def call(**kw):
+        a = dict(args, **kw)
+        return lib.vlpk_embed_tables_bwd(a["B"], a["L"], a["H"], a["R"], a["vis"], 4096, 4096, None, 8192, a["V"], a["P"], a["T"], 12288, 16384,
+                                         20480, 24576, None)
+    assert call(T=9) < 0 and b"token types" in lib.vlpk_last_error()
+    assert call(R=15) < 0 and b"do not fit" in lib.vlpk_last_error()
+    assert call(H=100) < 0

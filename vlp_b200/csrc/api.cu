@@ -14,6 +14,7 @@
 #include "host.cuh"
 #include "optim.cuh"
 #include "rowops.cuh"
+#include "tables.cuh"
 
 using namespace vlpk;
 typedef __nv_bfloat16 bf16;
@@ -410,6 +411,21 @@ int vlpk_embed_bwd(int B, int L, int H, int R, int vis_input, const int64_t* ids
   a.dgamma = d_ln_g; a.dbeta = d_ln_b;
   a.drop = mk_drop(drop, drop ? drop->p : 0.f, site);
   return launch_embed_bwd(a, S(stream));
+}
+
+int vlpk_embed_tables_bwd(int B, int L, int H, int R, int vis_input, const int64_t* ids, const int64_t* token_type, const int64_t* pos,
+                          const void* dz, int V, int P, int T, void* d_word, float* word_scratch, float* d_pos, float* d_type,
+                          void* stream) {
+  TableGradArgs a;
+  a.B = B; a.L = L; a.H = H; a.R = R; a.vis_input = vis_input;
+  a.V = V; a.P = P; a.T = T;
+  a.ids = reinterpret_cast<const long long*>(ids);
+  a.tt = reinterpret_cast<const long long*>(token_type);
+  a.pos = reinterpret_cast<const long long*>(pos);
+  a.dz = static_cast<const bf16*>(dz);
+  a.d_word = static_cast<bf16*>(d_word);
+  a.scratch = word_scratch; a.d_pos = d_pos; a.d_type = d_type;
+  return launch_embed_tables_bwd(a, S(stream));
 }
 
 int vlpk_ln_res_drop_fwd(int64_t M, int H, const void* t, const void* res, const void* gamma, const void* beta, void* y, float* stats,

@@ -6,6 +6,7 @@ these ops anywhere in the package, so a missing library is a hard error.
 """
 import ctypes as C
 import itertools
+import os
 
 import torch
 
@@ -26,6 +27,9 @@ def set_device_seed_tensor(t):
     global _seed_dev
     _seed_dev = t
 
+
+# opt-in (not yet run on a B200): embedding-table gradients by vlpk_embed_tables_bwd instead of torch index_add_ (csrc/tables.cu)
+FUSED_TABLE_GRADS = os.environ.get("VLP_FUSED_TABLE_GRADS", "0") == "1"
 
 _encoder_grad_hook = None  # data parallelism: callable(flat_gradient_arena) invoked by EncoderStackFn.backward (vlp_b200/dp.py)
 
@@ -327,15 +331,25 @@ class EmbedFn(torch.autograd.Function):
         L.call("vlpk_embed_bwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), tabs[0].data_ptr(), tabs[1].data_ptr(),
                tabs[2].data_ptr(), L.ptr(visc), L.ptr(vpec), tabs[3].data_ptr(), stats.data_ptr(), dyc.data_ptr(), dz.data_ptr(), dg.data_ptr(),
                db.data_ptr(), drop, 1 << 20, L.stream())
+        d_vis = dz[:, 1:R + 1] if vis_input else None
+        if FUSED_TABLE_GRADS:                                  # opt-in: one library call instead of the torch scatter below
+            V, P, T = tabs[0].shape[0], tabs[1].shape[0], tabs[2].shape[0]
+            d_word = torch.empty(V, H, device=dev, dtype=BF16)
+            scratch = torch.empty(V, H, device=dev, dtype=torch.float32)
+            d_pos = torch.zeros(P, H, device=dev, dtype=torch.float32)
+            d_type = torch.zeros(T, H, device=dev, dtype=torch.float32)
+            L.call("vlpk_embed_tables_bwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), dz.data_ptr(), V, P, T,
+                   d_word.data_ptr(), scratch.data_ptr(), d_pos.data_ptr(), d_type.data_ptr(), L.stream())
+            out = [None if d_vis is None else d_vis.to(dts[0]), None if d_vis is None else d_vis.to(dts[1]), d_word.to(dts[2]), d_pos.to(dts[3]),
+                   d_type.to(dts[4]), dg.to(dts[5]), db.to(dts[6])]
+            return tuple(out) + (None,) * 7
         # scatter of the pre-LN gradient: region rows go to the projections, the other rows to the tables
         if vis_input:
-            d_vis = dz[:, 1:R + 1]
             keep = torch.cat((torch.zeros(1, dtype=torch.long, device=dev), torch.arange(R + 1, Lq, device=dev)))
             dz_tab = dz[:, keep].reshape(-1, H).float()
             ids_tab = ids[:, keep].reshape(-1)
             pos_tab = (pos[:, keep] if pos is not None else keep.unsqueeze(0).expand(B, -1)).reshape(-1)
         else:
-            d_vis = None
             dz_tab = dz.reshape(-1, H).float()
             ids_tab = ids.reshape(-1)
             pos_tab = (pos if pos is not None else torch.arange(Lq, device=dev).unsqueeze(0).expand(B, -1)).reshape(-1)
