@@ -105,6 +105,10 @@ int vlpk_version(void);
 const char* vlpk_last_error(void);
 /* bring-up / A-B testing only: force the GEMM CTA-group size (0 = cost model, 1 = single CTA tiles, 2 = CTA pairs). */
 void vlpk_debug_set_cta_group(int cg);
+/* Leave n SMs out of the persistent GEMM grids (and of the tile cost model) from now on; 0 restores the full machine.  For
+ * data-parallel callers while a collective that owns SMs (NCCL all-reduce of the previous gradient arena) runs beside the
+ * backward GEMMs: a grid sized for all SMs would have its last CTAs wait behind the collective's. */
+void vlpk_set_reserved_sms(int n);
 /* host-only: the (tile N, CTA-group size, split-K) the cost model picks for a GEMM; out3 = {bn, cg, splits}.  No GPU needed. */
 int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int seg_rows, int epi, int bn, int splits, int* out3);
 

@@ -382,3 +382,20 @@ def test_embed_tables_bwd_argument_validation():
     assert call(T=9) < 0 and b"token types" in lib.vlpk_last_error()
     assert call(R=15) < 0 and b"do not fit" in lib.vlpk_last_error()
     assert call(H=100) < 0
+
+
+def test_reserved_sms_shrinks_the_gemm_plan_and_restores():
+    """vlpk_set_reserved_sms (data-parallel experiment): the cost model plans for the reduced machine; 0 restores it."""
+    lib = _lib.lib()
+    M = 64 * 123
+    full = [_plan(n, k, M, a_mn=1, b_mn=1, epi=6, splits=0) for (n, k) in ((768, 3072), (2304, 768))]
+    try:
+        lib.vlpk_set_reserved_sms(16)                          # 148 -> 132 SMs = 66 CTA pairs
+        for (n, k) in ((768, 3072), (2304, 768)):
+            bn, cg, s = _plan(n, k, M, a_mn=1, b_mn=1, epi=6, splits=0)
+            tiles = ((n + 128 * cg - 1) // (128 * cg)) * ((k + bn - 1) // bn) * s
+            slots = 132 // cg
+            assert tiles / (-(-tiles // slots) * slots) >= 0.85          # the last round of the REDUCED machine is well filled
+    finally:
+        lib.vlpk_set_reserved_sms(0)
+    assert [_plan(n, k, M, a_mn=1, b_mn=1, epi=6, splits=0) for (n, k) in ((768, 3072), (2304, 768))] == full

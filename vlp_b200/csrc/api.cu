@@ -333,6 +333,7 @@ int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int 
   g.epi = epi; g.bn = bn; g.splits = splits;
   return plan_gemm(g, &out3[0], &out3[1], &out3[2]);
 }
+void vlpk_set_reserved_sms(int n) { set_reserved_sms(n); }
 const char* vlpk_last_error(void) { return get_error(); }
 
 int vlpk_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, int64_t stride_b, int64_t stride_r, uint32_t* out,

@@ -523,7 +523,7 @@ static int launch_inst(const GemmTmaps& tm, const GemmArgs& args, int num_work, 
     VLPK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
     attr_set = true;
   }
-  const int max_clusters = num_sms() / CG;
+  const int max_clusters = gemm_sms() / CG;
   const int clusters = num_work < max_clusters ? num_work : max_clusters;
   LaunchScope scope(A_MN ? CAT_GEMM_WGRAD : (B_MN ? CAT_GEMM_DGRAD : CAT_GEMM_FWD), 2.0 * args.M * args.N * args.K, stream);
   VLPK_CUDA(launch_ex(kfn, dim3(clusters * CG), dim3(NUM_THREADS), L::DYN_BYTES, stream, CG, tm, args));
@@ -575,7 +575,7 @@ static double tile_cost(int M, int N, int total_kb, int bn, int cg, int splits, 
   const int num_m = (M + BM * cg - 1) / (BM * cg);
   const int num_n = (N + bn - 1) / bn;
   const long long tiles = static_cast<long long>(num_m) * num_n * splits;
-  const int slots = num_sms() / cg;
+  const int slots = gemm_sms() / cg;
   const long long rounds = (tiles + slots - 1) / slots;
   const int kb_per = (total_kb + splits - 1) / splits;
   const double mainloop = kb_per * (128.0 + double(bn) / cg);

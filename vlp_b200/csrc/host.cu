@@ -91,6 +91,17 @@ int num_sms() {
   return n;
 }
 
+// SMs the persistent GEMM grids may occupy.  A data-parallel caller can reserve some for a concurrently running collective
+// (vlpk_set_reserved_sms): a persistent grid sized for all SMs would otherwise leave its last CTAs waiting behind the
+// collective's CTAs and finish a full tile-loop late.
+static int g_reserved_sms = 0;
+void set_reserved_sms(int n) { g_reserved_sms = n > 0 ? n : 0; }
+int gemm_sms() {
+  int n = num_sms() - g_reserved_sms;
+  if (n < 2) n = 2;
+  return n & ~1;  // CTA pairs
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch accounting / profiling
 // ------------------------------------------------------------------------------------------------

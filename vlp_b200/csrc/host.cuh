@@ -56,6 +56,9 @@ inline int make_tmap_2d(CUtensorMap* out, TmapDtype dt, const void* base, uint64
 }
 
 int num_sms();
+// SMs available to the persistent GEMM grids: num_sms() minus what vlpk_set_reserved_sms put aside (default 0), even.
+int gemm_sms();
+void set_reserved_sms(int n);
 
 // Launch with optional cluster dimension and programmatic dependent launch (VLPK_PDL=0 disables the latter).
 bool pdl_enabled();

@@ -7,14 +7,20 @@ NCCL (`all_reduce`, AVG, asynchronously, the moment the group's backward finishe
 no per-parameter bucket copies, no autograd hooks, no graph walk for unused parameters.  The few remaining parameters
 (embeddings, region projections, heads) are reduced as one flattened buffer after backward.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
+from . import _lib as L
 from . import ops
 
 
 class GradientAllReducer:
-    def __init__(self, model, group=None, layers_per_call=3):
+    def __init__(self, model, group=None, layers_per_call=3, reserved_sms=None):
+        """reserved_sms (experiment, default 0 / env VLP_DP_RESERVED_SMS): while an arena all-reduce is in flight the persistent
+        GEMM grids launched after it leave that many SMs to NCCL's CTAs (vlpk_set_reserved_sms); restored by finish()."""
+        self.reserved_sms = int(os.environ.get("VLP_DP_RESERVED_SMS", "0")) if reserved_sms is None else int(reserved_sms)
         self.group = group
         self.world = dist.get_world_size(group)
         self.model = model
@@ -42,6 +48,8 @@ class GradientAllReducer:
         w = self._reduce(arena, async_op=True)
         if w is not None:
             self._works.append(w)
+        if self.reserved_sms > 0:
+            L.lib().vlpk_set_reserved_sms(self.reserved_sms)
 
     def finish(self):
         """After loss.backward(): reduce the non-encoder gradients and wait for everything in flight."""
@@ -54,6 +62,8 @@ class GradientAllReducer:
         for w in self._works:
             w.wait()
         self._works.clear()
+        if self.reserved_sms > 0:
+            L.lib().vlpk_set_reserved_sms(0)
 
     def close(self):
         ops.set_encoder_grad_hook(None)
