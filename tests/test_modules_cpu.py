@@ -179,13 +179,13 @@ def test_workspace_bytes_matches_the_python_allocations():
     """vlpk_workspace_bytes (host-only) vs what vlp_b200/ops.py allocates for the same shape."""
     import ctypes as C
     from vlp_b200 import ops
-    for (B, Lq, Lkv, H, heads, I) in ((2, 15, 15, 128, 2, 512), (64, 123, 123, 768, 12, 3072), (3, 2, 77, 128, 2, 512)):
+    for (B, Lq, Lkv, H, heads, I) in ((2, 15, 15, 128, 2, 512), (64, 123, 123, 768, 12, 3072), (3, 2, 77, 128, 2, 512), (1, 123, 123, 64, 1, 256)):
         out = (C.c_size_t * 3)()
         shape = _lib.VlpkShape(B, Lq, Lkv, H, heads, I)
         assert _lib.lib().vlpk_workspace_bytes(C.byref(shape), out) == 0
         M = B * Lq
         bf = M * 3 * H + 5 * M * H + 2 * M * I + (B * Lkv * 2 * H if Lkv != Lq else 0)
-        f32 = B * heads * Lq + 4 * M
+        f32 = (B * heads * Lq + 3) // 4 * 4 + 4 * M
         assert out[0] == 2 * bf + 4 * f32
         assert out[1] == 2 * (7 * M * H + M * I + 3 * M * H)
         assert out[2] == 4 * sum(ops._layer_sizes(H, I))
@@ -399,3 +399,16 @@ def test_reserved_sms_shrinks_the_gemm_plan_and_restores():
     finally:
         lib.vlpk_set_reserved_sms(0)
     assert [_plan(n, k, M, a_mn=1, b_mn=1, epi=6, splits=0) for (n, k) in ((768, 3072), (2304, 768))] == full
+
+
+def test_row_kernels_reject_misaligned_pointers_before_launching():
+    """16-byte vector access is a precondition of the row kernels: a misaligned pointer is an argument error (rc < 0, nothing
+    launched, SURVEY.md §8b error convention), not a device fault."""
+    lib = _lib.lib()
+    ok = [4096 * i for i in range(1, 9)]
+    assert lib.vlpk_ln_res_drop_fwd(4, 128, ok[0] + 2, ok[1], ok[2], ok[3], ok[4], ok[5], None, 0, None) < 0
+    assert b"16-byte aligned" in lib.vlpk_last_error()
+    assert lib.vlpk_ln_res_drop_fwd(4, 128, ok[0], ok[1], ok[2], ok[3], ok[4], ok[5] + 4, None, 0, None) < 0        # stats: float2
+    assert lib.vlpk_ln_res_drop_bwd(4, 128, ok[0], ok[1], ok[2], ok[3], ok[4] + 8, ok[5], None, ok[6], ok[7], None, None, 0, None) < 0
+    assert lib.vlpk_colsum(ok[0] + 6, 128, 4, 128, ok[1], None) < 0
+    assert lib.vlpk_ln_res_drop_fwd(4, 100, ok[0], ok[1], ok[2], ok[3], ok[4], ok[5], None, 0, None) < 0             # H % 8

@@ -543,7 +543,8 @@ int vlpk_workspace_bytes(const VlpkShape* s, size_t* out3) {
   VLPK_CHECK_ARG(out3 != nullptr, "workspace_bytes: null output");
   const size_t H = s->H, I = s->I, Mq = static_cast<size_t>(s->B) * s->Lq, Mkv = static_cast<size_t>(s->B) * s->Lkv;
   const size_t kv = (s->Lkv != s->Lq) ? Mkv * 2 * H : 0;
-  out3[0] = 2 * (Mq * (3 * H + 5 * H + 2 * I) + kv) + 4 * (static_cast<size_t>(s->B) * s->heads * s->Lq + 4 * Mq);
+  const size_t lse = (static_cast<size_t>(s->B) * s->heads * s->Lq + 3) / 4 * 4;  // keeps the float2 statistics behind it aligned
+  out3[0] = 2 * (Mq * (3 * H + 5 * H + 2 * I) + kv) + 4 * (lse + 4 * Mq);
   out3[1] = 2 * (Mq * (7 * H + I + 3 * H));
   out3[2] = 4 * (3 * H * H + 3 * H + H * H + H + 2 * H + I * H + I + H * I + H + 2 * H);
   return 0;

@@ -253,9 +253,17 @@ __global__ void __launch_bounds__(LNB_WARPS * 32, 1) ln_res_drop_bwd_kernel(LnAr
     else { constexpr int NCH = 4; __VA_ARGS__; }   \
   } while (0)
 
+// every bf16 row pointer is read / written with 16-byte vectors, stats as float2: misalignment must be an argument error,
+// not a device fault (null = absent)
+static inline bool misaligned(const void* p, unsigned mask) { return (reinterpret_cast<uintptr_t>(p) & mask) != 0; }
+
 static int check_ln(const LnArgs& a) {
   VLPK_CHECK_ARG(a.M > 0 && a.H > 0 && a.H % 8 == 0 && a.H <= MAXCH * 256, "layernorm: H=%d must be a multiple of 8 and <= %d",
                  a.H, MAXCH * 256);
+  VLPK_CHECK_ARG(!(misaligned(a.t, 15) || misaligned(a.res, 15) || misaligned(a.gamma, 15) || misaligned(a.beta, 15) || misaligned(a.y, 15) ||
+                   misaligned(a.dy, 15) || misaligned(a.dz, 15) || misaligned(a.dt, 15) || misaligned(a.stats, 7) ||
+                   misaligned(a.dgamma, 3) || misaligned(a.dbeta, 3) || misaligned(a.dbias, 3)),
+                 "layernorm: bf16 buffers must be 16-byte aligned (stats 8, fp32 accumulators 4)");
   return 0;
 }
 
@@ -435,6 +443,10 @@ static int check_embed(const EmbedArgs& a) {
   VLPK_CHECK_ARG(a.B > 0 && a.L > 0 && a.H > 0 && a.H % 8 == 0 && a.H <= MAXCH * 256, "embed: bad shape B=%d L=%d H=%d", a.B,
                  a.L, a.H);
   VLPK_CHECK_ARG(!a.vis_input || (a.vis != nullptr && a.vpe != nullptr && a.R + 1 <= a.L), "embed: vis_input needs vis/vpe and R+1<=L");
+  VLPK_CHECK_ARG(!(misaligned(a.word, 15) || misaligned(a.posw, 15) || misaligned(a.typew, 15) || misaligned(a.vis, 15) || misaligned(a.vpe, 15) ||
+                   misaligned(a.gamma, 15) || misaligned(a.beta, 15) || misaligned(a.y, 15) || misaligned(a.dy, 15) || misaligned(a.dz, 15) ||
+                   misaligned(a.stats, 7) || misaligned(a.ids, 7) || misaligned(a.tt, 7) || misaligned(a.pos, 7)),
+                 "embed: bf16 buffers must be 16-byte aligned (ids / stats 8)");
   return 0;
 }
 
@@ -553,6 +565,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 
 int launch_colsum(const void* x, long long ld, long long M, int N, float* out, cudaStream_t s) {
   VLPK_CHECK_ARG(N % 8 == 0 && ld % 8 == 0, "colsum: N=%d ld=%lld must be multiples of 8", N, ld);
+  VLPK_CHECK_ARG(M > 0 && !misaligned(x, 15) && !misaligned(out, 3), "colsum: M=%lld, x must be 16-byte aligned", M);
   dim3 grid((N + 63) / 64, static_cast<unsigned>((M + COLSUM_ROWS - 1) / COLSUM_ROWS));
   LaunchScope scope(CAT_MISC, 2.0 * M * N, s);
   colsum_kernel<<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(x), ld, M, N, out);

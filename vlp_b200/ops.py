@@ -116,7 +116,8 @@ class _Acts:
                          ("y", M * H)]
         if Lkv is not None:
             self.bf_sizes.append(("kv", B * Lkv * 2 * H))
-        self.f_sizes = [("lse", B * heads * Lq), ("stats1", 2 * M), ("stats2", 2 * M)]
+        # lse rounded up to 4 floats so that the float2 statistics behind it stay 8-byte aligned for odd B * heads * Lq
+        self.f_sizes = [("lse", (B * heads * Lq + 3) // 4 * 4), ("stats1", 2 * M), ("stats2", 2 * M)]
         per_bf = sum(s for _, s in self.bf_sizes)
         per_f = sum(s for _, s in self.f_sizes)
         self.bf = torch.empty(n_layers, per_bf, device=device, dtype=BF16)
