@@ -512,6 +512,7 @@ __global__ void mask_pack_kernel(const T* m, long long sb, long long sr, int B, 
 int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, long long stride_b, long long stride_r,
                      uint32_t* out, cudaStream_t s) {
   VLPK_CHECK_ARG(B > 0 && rows > 0 && kv > 0 && kv <= 128, "mask_pack: kv=%d must be in [1,128]", kv);
+  VLPK_CHECK_ARG(!misaligned(out, 15), "mask_pack: the bitmask buffer must be 16-byte aligned");
   const long long n = static_cast<long long>(B) * rows;
   const unsigned grid = static_cast<unsigned>((n + 127) / 128);
   LaunchScope scope(CAT_MISC, 0.0, s);
