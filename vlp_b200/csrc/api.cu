@@ -108,15 +108,22 @@ WgradSide* wgrad_side() {
   return enabled ? &side : nullptr;
 }
 
-// wgrad_linear that may run beside the kernels issued on `main` after it; wgrad_join(main) must follow before its inputs are reused.
-int wgrad_overlapped(int M, int N, int K, const void* dy, int64_t lddy, const void* x, int64_t ldx, float* dw, int64_t lddw,
-                     cudaStream_t main) {
+// One Linear's backward: weight gradient + input gradient, which only share their inputs.  Default: wgrad then dgrad on `main`
+// (the order validated on the B200).  With the side stream: dgrad first on `main` (it is on the critical path and takes the
+// SMs), then the wgrad on the side stream, whose CTAs fill the SMs the dgrad's partial last wave leaves idle and overlap whatever
+// `main` issues next.  wgrad_join(main) must follow before the wgrad's inputs are overwritten.
+template <class WgradFn, class DgradFn>
+int linear_bwd_pair(cudaStream_t main, WgradFn&& wgrad, DgradFn&& dgrad) {
   WgradSide* sd = wgrad_side();
-  if (sd == nullptr) return wgrad_linear(M, N, K, dy, lddy, x, ldx, dw, lddw, main);
-  VLPK_CUDA(cudaEventRecord(sd->fork, main));
+  if (sd == nullptr) {
+    VLPK_TRY(wgrad(main));
+    return dgrad(main);
+  }
+  VLPK_CUDA(cudaEventRecord(sd->fork, main));  // everything both kernels read has been issued on `main` by now
   VLPK_CUDA(cudaStreamWaitEvent(sd->stream, sd->fork, 0));
+  VLPK_TRY(dgrad(main));
   sd->pending = true;
-  return wgrad_linear(M, N, K, dy, lddy, x, ldx, dw, lddw, sd->stream);
+  return wgrad(sd->stream);
 }
 
 int wgrad_join(cudaStream_t main) {
@@ -220,11 +227,13 @@ int ffn_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const VlpkLayerA
   VLPK_TRY(launch_ln_res_drop_bwd(l2, st));
   const void* dt2 = hdrop ? ws->dt2 : ws->dz2;
   // ---- output.dense: dW2 += dt2^T hmid ; dU = (dt2 W2) * gelu'(u)   [gelu'(u) was stored by the forward epilogue in acts.u]
-  VLPK_TRY(wgrad_overlapped(M, H, I, dt2, H, a->hmid, I, g->w2, I, st));
-  VLPK_TRY(dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, st, g->b1));  // + db1 = column sums of dU
+  VLPK_TRY(linear_bwd_pair(
+      st, [&](cudaStream_t q) { return wgrad_linear(M, H, I, dt2, H, a->hmid, I, g->w2, I, q); },
+      [&](cudaStream_t q) { return dgrad_linear(M, H, I, dt2, H, w->w2, I, ws->du, I, EPI_MUL, a->u, I, q, g->b1); }));  // + db1 = column sums of dU
   // ---- intermediate.dense: dW1 += dU^T y1 ; dy1 = dU W1 + dz2 (residual branch of LN2)
-  VLPK_TRY(wgrad_overlapped(M, I, H, ws->du, I, a->y1, H, g->w1, H, st));
-  VLPK_TRY(dgrad_linear(M, I, H, ws->du, I, w->w1, H, dy1, H, EPI_ADD, ws->dz2, H, st));
+  VLPK_TRY(linear_bwd_pair(
+      st, [&](cudaStream_t q) { return wgrad_linear(M, I, H, ws->du, I, a->y1, H, g->w1, H, q); },
+      [&](cudaStream_t q) { return dgrad_linear(M, I, H, ws->du, I, w->w1, H, dy1, H, EPI_ADD, ws->dz2, H, q); }));
   return wgrad_join(st);
 }
 
@@ -249,8 +258,9 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   VLPK_TRY(launch_ln_res_drop_bwd(l1, st));
   const void* dt1 = hdrop ? ws->dt1 : ws->dz1;
   // ---- attention.output.dense
-  VLPK_TRY(wgrad_overlapped(M, H, H, dt1, H, a->ctx, H, g->wo, H, st));
-  VLPK_TRY(dgrad_linear(M, H, H, dt1, H, w->wo, H, ws->dctx, H, EPI_STORE, nullptr, 0, st));
+  VLPK_TRY(linear_bwd_pair(
+      st, [&](cudaStream_t q) { return wgrad_linear(M, H, H, dt1, H, a->ctx, H, g->wo, H, q); },
+      [&](cudaStream_t q) { return dgrad_linear(M, H, H, dt1, H, w->wo, H, ws->dctx, H, EPI_STORE, nullptr, 0, q); }));
   // ---- attention core
   AttnDesc ad;
   ad.B = s->B; ad.heads = s->heads; ad.Lq = s->Lq; ad.Lkv = s->Lkv;
@@ -264,7 +274,6 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   ad.dbias = g->bqkv;   // d bqkv = column sums of dQ | dK | dV, folded inside the attention backward kernel
   VLPK_TRY(launch_attn_bwd(ad, st));
   // ---- QKV projection: dWqkv += dqkv^T x ; dx = dqkv Wqkv + dz1 (residual branch of LN1)
-  VLPK_TRY(wgrad_overlapped(M, 3 * H, H, ws->dqkv, 3 * H, x, H, g->wqkv, H, st));
   GemmDesc d;
   d.M = M; d.N = H; d.K = 3 * H;
   d.A = ws->dqkv; d.lda = 3 * H;
@@ -273,7 +282,9 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   d.D0 = dx; d.ldd0 = H;
   d.epi = EPI_ADD;
   d.aux = static_cast<const bf16*>(ws->dz1); d.ld_aux = H;
-  VLPK_TRY(launch_gemm(d, st));
+  VLPK_TRY(linear_bwd_pair(
+      st, [&](cudaStream_t q) { return wgrad_linear(M, 3 * H, H, ws->dqkv, 3 * H, x, H, g->wqkv, H, q); },
+      [&](cudaStream_t q) { return launch_gemm(d, q); }));
   return wgrad_join(st);
 }
 
