@@ -412,3 +412,20 @@ def test_row_kernels_reject_misaligned_pointers_before_launching():
     assert lib.vlpk_ln_res_drop_bwd(4, 128, ok[0], ok[1], ok[2], ok[3], ok[4] + 8, ok[5], None, ok[6], ok[7], None, None, 0, None) < 0
     assert lib.vlpk_colsum(ok[0] + 6, 128, 4, 128, ok[1], None) < 0
     assert lib.vlpk_ln_res_drop_fwd(4, 100, ok[0], ok[1], ok[2], ok[3], ok[4], ok[5], None, 0, None) < 0             # H % 8
+
+
+def test_wave_remainder_split_plan():
+    """VLPK_GEMM_TAIL_SPLIT experiment (csrc/gemm.cu plan_tail_split): which hot GEMMs would be split and where."""
+    split = _lib.lib().vlpk_debug_plan_tail_split
+    M = 64 * 123
+    # N = 768 dgrads: 93 pair-tiles on 74 pairs -> 24 row blocks (72 tiles) lead, 1 728 rows follow with 128-wide tiles
+    assert split(M, 768, 3072, 0, 1, 3, 256, 2, 1) == 24 * 256
+    assert split(M, 768, 768, 0, 1, 0, 256, 2, 1) == 24 * 256
+    # FFN-up / dU: 372 tiles = 5 rounds + 2 tiles -> 30 row blocks lead
+    assert split(M, 3072, 768, 0, 0, 1, 256, 2, 1) == 30 * 256
+    assert split(M, 3072, 768, 0, 1, 4, 256, 2, 1) == 30 * 256
+    # well-filled last rounds, weight gradients (split-K) and Philox epilogues are left alone
+    assert split(M, 2304, 768, 0, 0, 0, 256, 2, 1) == 0
+    assert split(M, 768, 768, 0, 0, 0, 192, 2, 1) == 0
+    assert split(768, 3072, M, 1, 1, 6, 256, 2, 5) == 0
+    assert split(6400, 2048, 2048, 0, 0, 2, 256, 2, 1) == 0

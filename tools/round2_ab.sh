@@ -6,7 +6,7 @@
 cd "$(dirname "$0")/.." || exit 1
 mkdir -p gpurun_out
 : > gpurun_out/r02_unverified_tests.log
-for f in tests/test_zz_abi_split_gpu.py tests/test_zz_bertadam_gpu.py tests/test_zz_fused_head_gpu.py tests/test_zz_table_grads_gpu.py; do
+for f in tests/test_zz_abi_split_gpu.py tests/test_zz_bertadam_gpu.py tests/test_zz_fused_head_gpu.py tests/test_zz_table_grads_gpu.py tests/test_zz_tail_split_gpu.py; do
   echo "=== $f" >> gpurun_out/r02_unverified_tests.log
   VLP_RUN_UNVERIFIED=1 timeout 600 python -m pytest "$f" -q -m gpu -p no:cacheprovider >> gpurun_out/r02_unverified_tests.log 2>&1
   echo "exit=$?" >> gpurun_out/r02_unverified_tests.log
@@ -25,5 +25,6 @@ run baseline          VLP_AB=0
 run wgrad_stream      VLPK_WGRAD_STREAM=1
 run fused_head        VLP_FUSED_HEAD=1
 run fused_tables      VLP_FUSED_TABLE_GRADS=1
-run all               VLPK_WGRAD_STREAM=1 VLP_FUSED_HEAD=1 VLP_FUSED_TABLE_GRADS=1
+run tail_split        VLPK_GEMM_TAIL_SPLIT=1
+run all               VLPK_WGRAD_STREAM=1 VLP_FUSED_HEAD=1 VLP_FUSED_TABLE_GRADS=1 VLPK_GEMM_TAIL_SPLIT=1
 run baseline_again    VLP_AB=0

@@ -336,6 +336,7 @@ extern "C" {
 
 int vlpk_version(void) { return VLPK_VERSION; }
 void vlpk_debug_set_cta_group(int cg) { debug_set_cta_group(cg); }
+void vlpk_debug_set_tail_split(int on) { debug_set_tail_split(on); }
 int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int seg_rows, int epi, int bn, int splits, int* out3) {
   GemmDesc g;
   g.M = M; g.N = N; g.K = K;
@@ -345,6 +346,13 @@ int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int 
   return plan_gemm(g, &out3[0], &out3[1], &out3[2]);
 }
 void vlpk_set_reserved_sms(int n) { set_reserved_sms(n); }
+int vlpk_debug_plan_tail_split(int M, int N, int K, int a_mn, int b_mn, int epi, int bn, int cg, int splits) {
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K;
+  g.a_mn = a_mn != 0; g.b_mn = b_mn != 0;
+  g.epi = epi;
+  return plan_tail_split(g, bn, cg, splits);
+}
 const char* vlpk_last_error(void) { return get_error(); }
 
 int vlpk_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, int64_t stride_b, int64_t stride_r, uint32_t* out,
