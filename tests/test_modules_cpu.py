@@ -429,3 +429,10 @@ def test_wave_remainder_split_plan():
     assert split(M, 768, 768, 0, 0, 0, 192, 2, 1) == 0
     assert split(768, 3072, M, 1, 1, 6, 256, 2, 5) == 0
     assert split(6400, 2048, 2048, 0, 0, 2, 256, 2, 1) == 0
+
+
+def test_debug_options_are_named_and_default_off():
+    lib = _lib.lib()
+    for name in (b"tail_split", b"wgrad_stream", b"mask_pack_warp"):
+        assert lib.vlpk_debug_set_option(name, 0) == 0
+    assert lib.vlpk_debug_set_option(b"no_such_option", 1) < 0 and b"unknown option" in lib.vlpk_last_error()

@@ -26,5 +26,6 @@ run wgrad_stream      VLPK_WGRAD_STREAM=1
 run fused_head        VLP_FUSED_HEAD=1
 run fused_tables      VLP_FUSED_TABLE_GRADS=1
 run tail_split        VLPK_GEMM_TAIL_SPLIT=1
-run all               VLPK_WGRAD_STREAM=1 VLP_FUSED_HEAD=1 VLP_FUSED_TABLE_GRADS=1 VLPK_GEMM_TAIL_SPLIT=1
+run mask_pack_warp    VLPK_MASK_PACK_WARP=1
+run all               VLPK_WGRAD_STREAM=1 VLP_FUSED_HEAD=1 VLP_FUSED_TABLE_GRADS=1 VLPK_GEMM_TAIL_SPLIT=1 VLPK_MASK_PACK_WARP=1
 run baseline_again    VLP_AB=0

@@ -4,7 +4,7 @@
     python tools/sass_diff.py /tmp/val/vlp_b200/libvlpk.so vlp_b200/libvlpk.so
 
 Used at the end of round 1 (GPU budget spent) to show that the host-side refactors and the new opt-in kernels left every kernel
-that had been validated on the B200 byte-identical (63 / 63; 16 new kernels)."""
+that had been validated on the B200 byte-identical (63 / 63; 19 new kernels)."""
 import hashlib
 import re
 import subprocess
@@ -42,4 +42,7 @@ def main(old, new):
 
 
 if __name__ == "__main__":
-    sys.exit(main(sys.argv[1], sys.argv[2]))
+    try:
+        sys.exit(main(sys.argv[1], sys.argv[2]))
+    except BrokenPipeError:
+        sys.exit(0)

@@ -7,6 +7,7 @@
 #include "../../include/vlpk.h"
 
 #include <cstdlib>
+#include <cstring>
 
 #include "attn.cuh"
 #include "gemm.cuh"
@@ -94,18 +95,22 @@ struct WgradSide {
   bool pending = false;
 };
 
+int g_wgrad_stream = -1;  // -1: take VLPK_WGRAD_STREAM from the environment on first use (vlpk_debug_set_option "wgrad_stream")
+
 WgradSide* wgrad_side() {
-  static int enabled = -1;
   static WgradSide side;
-  if (enabled < 0) {
+  if (g_wgrad_stream < 0) {
     const char* e = getenv("VLPK_WGRAD_STREAM");
-    enabled = (e != nullptr && e[0] == '1') ? 1 : 0;
-    if (enabled && (cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming) != cudaSuccess))
-      enabled = 0;
+    g_wgrad_stream = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  return enabled ? &side : nullptr;
+  if (g_wgrad_stream == 1 && side.stream == nullptr &&
+      (cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+       cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming) != cudaSuccess ||
+       cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming) != cudaSuccess)) {
+    side.stream = nullptr;
+    g_wgrad_stream = 0;
+  }
+  return g_wgrad_stream == 1 ? &side : nullptr;
 }
 
 // One Linear's backward: weight gradient + input gradient, which only share their inputs.  Default: wgrad then dgrad on `main`
@@ -336,7 +341,14 @@ extern "C" {
 
 int vlpk_version(void) { return VLPK_VERSION; }
 void vlpk_debug_set_cta_group(int cg) { debug_set_cta_group(cg); }
-void vlpk_debug_set_tail_split(int on) { debug_set_tail_split(on); }
+int vlpk_debug_set_option(const char* name, int value) {
+  VLPK_CHECK_ARG(name != nullptr, "set_option: null name");
+  if (strcmp(name, "tail_split") == 0) { debug_set_tail_split(value); return 0; }
+  if (strcmp(name, "mask_pack_warp") == 0) { set_mask_pack_warp(value); return 0; }
+  if (strcmp(name, "wgrad_stream") == 0) { g_wgrad_stream = value ? 1 : 0; return 0; }
+  set_error("set_option: unknown option '%s'", name);
+  return -1;
+}
 int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int seg_rows, int epi, int bn, int splits, int* out3) {
   GemmDesc g;
   g.M = M; g.N = N; g.K = K;
