@@ -436,3 +436,25 @@ def test_debug_options_are_named_and_default_off():
     for name in (b"tail_split", b"wgrad_stream", b"mask_pack_warp"):
         assert lib.vlpk_debug_set_option(name, 0) == 0
     assert lib.vlpk_debug_set_option(b"no_such_option", 1) < 0 and b"unknown option" in lib.vlpk_last_error()
+
+
+def test_encoder_layer_groups_dry_run():
+    """BertEncoder.layers_per_call: None (one fused call), k (uniform groups) or explicit sizes — one vlpk_encoder_fwd/bwd per group."""
+    import pytest
+    from tools import abi_cases
+    d = synth.TINY
+    cfg = vm.BertConfig(d.vocab, hidden_size=d.hidden, num_hidden_layers=5, num_attention_heads=d.heads, intermediate_size=d.inter,
+                        type_vocab_size=d.type_vocab, max_position_embeddings=d.max_pos, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    enc = vm.BertEncoder(cfg).bfloat16()
+    x = torch.randn(2, d.seq_len, d.hidden).bfloat16().requires_grad_(True)
+    mask = torch.zeros(2, 1, 1, d.seq_len)
+    for setting, n_calls in ((None, 1), (2, 3), ([1, 1, 3], 3), ((2, 3), 2)):
+        enc.layers_per_call = setting
+        with abi_cases.dry_run() as calls:
+            outs = enc(x, mask, output_all_encoded_layers=True)
+            outs[-1].float().sum().backward()
+        assert len(outs) == 5
+        assert calls.count("vlpk_encoder_fwd") == n_calls and calls.count("vlpk_encoder_bwd") == n_calls
+    enc.layers_per_call = [2, 2]
+    with pytest.raises(ValueError), abi_cases.dry_run():
+        enc(x, mask)

@@ -20,3 +20,5 @@ run reserve24      VLP_DP_RESERVED_SMS=24
 run ctas8          NCCL_MAX_CTAS=8
 run ctas8_res8     NCCL_MAX_CTAS=8 VLP_DP_RESERVED_SMS=8
 run ctas16_res16   NCCL_MAX_CTAS=16 VLP_DP_RESERVED_SMS=16
+run groups_1_2_3_3_3 VLP_DP_GROUPS=1,2,3,3,3
+run groups_2_2_4_4   VLP_DP_GROUPS=2,2,4,4

@@ -26,7 +26,8 @@ class GradientAllReducer:
         self.model = model
         self.backend = dist.get_backend(group)
         enc = model.bert.encoder
-        enc.layers_per_call = layers_per_call
+        groups = os.environ.get("VLP_DP_GROUPS")          # experiment: explicit group sizes from layer 0 up, e.g. "1,2,3,3,3"
+        enc.layers_per_call = [int(k) for k in groups.split(",")] if groups else layers_per_call
         enc_ids = {id(p) for p in enc.parameters()}
         self.other = [p for p in model.parameters() if p.requires_grad and id(p) not in enc_ids]
         ops.set_encoder_grad_hook(self._on_encoder_grads)

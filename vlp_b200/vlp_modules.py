@@ -241,7 +241,10 @@ class BertEncoder(nn.Module):
         super().__init__()
         layer = BertLayer(config)
         self.layer = nn.ModuleList([copy.deepcopy(layer) for _ in range(config.num_hidden_layers)])
-        self.layers_per_call = None   # None: the whole stack is one fused call; k: groups of k layers (DDP overlap)
+        # None: the whole stack is one fused call; k: groups of k layers; [k0, k1, ...]: explicit group sizes from layer 0 up
+        # (data parallelism: a group's gradients are complete — and their all-reduce can start — while lower layers still run
+        # backward; a small first group shortens the all-reduce that is exposed at the end of backward)
+        self.layers_per_call = None
 
     def forward(self, hidden_states, attention_mask, prev_embedding=None, prev_encoded_layers=None, output_all_encoded_layers=True):
         assert (prev_embedding is None) == (prev_encoded_layers is None), \
@@ -261,11 +264,19 @@ class BertEncoder(nn.Module):
         # gradients of the last group are complete (and their all-reduce bucket can start) while earlier layers still run backward
         bits = _mask_bits(attention_mask)
         n = len(self.layer)
-        step = n if not self.layers_per_call else max(1, int(self.layers_per_call))
+        if isinstance(self.layers_per_call, (list, tuple)):
+            sizes = [int(k) for k in self.layers_per_call]
+            if any(k < 1 for k in sizes) or sum(sizes) != n:
+                raise ValueError(f"layers_per_call={self.layers_per_call} must be positive group sizes summing to {n}")
+        else:
+            step = n if not self.layers_per_call else max(1, int(self.layers_per_call))
+            sizes = [min(step, n - s) for s in range(0, n, step)]
         dt = hidden_states.dtype
         outs, cur = [], hidden_states
-        for s in range(0, n, step):
-            group = self.layer[s:s + step]
+        s = 0
+        for size in sizes:
+            group = self.layer[s:s + size]
+            s += size
             params = []
             for l in group:
                 params.extend(l.flat_params())
