@@ -65,5 +65,7 @@ def test_model_with_fused_head_matches_default_head():
     assert abs(l0 - l1) < 2e-2 and rel(s1, s0) < 1e-2
     assert set(g0) == set(g1)
     for n in g0:
+        if "attention.self.key.bias" in n:       # exactly 0 in exact arithmetic (softmax shift invariance): pure rounding noise on both paths
+            continue
         if float(g0[n].norm()) > 0:
             assert rel(g1[n], g0[n]) < 5e-2, n
