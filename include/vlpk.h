@@ -111,13 +111,9 @@ void vlpk_debug_set_cta_group(int cg);
 void vlpk_set_reserved_sms(int n);
 /* host-only: the (tile N, CTA-group size, split-K) the cost model picks for a GEMM; out3 = {bn, cg, splits}.  No GPU needed. */
 int vlpk_debug_plan_gemm(int M, int N, int K, int a_mn, int b_mn, int nseg, int seg_rows, int epi, int bn, int splits, int* out3);
-/* bring-up / A-B testing only: switch an experimental host-side path on (1) or off (0) at run time; each also has an environment
- * default, all off: "tail_split" (VLPK_GEMM_TAIL_SPLIT, wave-remainder split of launch_gemm), "wgrad_stream" (VLPK_WGRAD_STREAM,
- * weight-gradient GEMMs on a side stream), "mask_pack_warp" (VLPK_MASK_PACK_WARP, warp-per-row mask packing).  < 0: unknown name. */
+/* A-B testing only: switch a host-side scheduling choice at run time.  "wgrad_stream" (default 1, env VLPK_WGRAD_STREAM=0 turns it
+ * off): the weight-gradient GEMM of each Linear's backward runs on a side stream behind its dgrad.  < 0: unknown name. */
 int vlpk_debug_set_option(const char* name, int value);
-/* host-only: rows given to the leading launch by the wave-remainder split experiment (VLPK_GEMM_TAIL_SPLIT=1; 0 = no split) for a
- * GEMM planned with tile N `bn`, CTA-group size `cg` and `splits`. */
-int vlpk_debug_plan_tail_split(int M, int N, int K, int a_mn, int b_mn, int epi, int bn, int cg, int splits);
 
 /* get_extended_attention_mask (modeling.py:807-833) -> per-row 128-bit "attend" bitmask.
  * mask: [B, rows, kv] with element strides (stride_b, stride_r, 1); rows may be 1 (2-D mask). out: [B, rows, 4] u32. */

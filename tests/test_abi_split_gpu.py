@@ -3,10 +3,9 @@ calls the module surface uses.  Call sequences live in tools/abi_cases.py (also 
 import pytest
 import torch
 
-from tools.gating import unverified_on_gpu
 from tools import abi_cases
 
-pytestmark = [pytest.mark.gpu, unverified_on_gpu]
+pytestmark = pytest.mark.gpu
 
 
 def test_ffn_bwd_plus_mha_bwd_equals_layer_bwd():

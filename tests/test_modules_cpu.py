@@ -227,8 +227,8 @@ def test_training_step_marshalling_dry_run():
                     b["is_next"], masked_pos=b["masked_pos"], masked_weights=b["masked_weights"], task_idx=b["task_idx"],
                     vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
         sum(l.float().sum() for l in out).backward()
-    assert calls == ["vlpk_linear_fwd"] * 3 + ["vlpk_embed_fwd", "vlpk_mask_pack", "vlpk_encoder_fwd", "vlpk_encoder_bwd", "vlpk_f32_to_bf16",
-                     "vlpk_embed_bwd"] + ["vlpk_linear_bwd"] * 3
+    assert calls == ["vlpk_linear_fwd"] * 3 + ["vlpk_embed_fwd", "vlpk_mask_pack", "vlpk_encoder_fwd", "vlpk_decoder_ce_fwd", "vlpk_decoder_ce_bwd",
+                     "vlpk_encoder_bwd", "vlpk_f32_to_bf16", "vlpk_embed_bwd", "vlpk_embed_tables_bwd"] + ["vlpk_linear_bwd"] * 3
     missing = [n for n, p in model.named_parameters() if p.grad is None]
     assert all(n.startswith("bert.pooler.") for n in missing), missing      # the img2txt loss never touches the pooler
     for n, p in model.named_parameters():
@@ -329,13 +329,12 @@ def test_bertadam_host_validation_in_the_library():
 
 
 def test_fused_mlm_head_marshalling_dry_run():
-    """Opt-in fused decoder + cross-entropy path (VLP_FUSED_HEAD=1 / model.fused_mlm_head): call sequence and gradient plumbing on
+    """Fused decoder + cross-entropy path (model.fused_mlm_head, the default): call sequence and gradient plumbing on
     CPU (values meaningless) — the tied decoder weight receives a gradient from both the head and the embedding lookup."""
     from tools import abi_cases
     d, cfg = _tiny_config()
     model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions).bfloat16().train()
-    assert model.fused_mlm_head is False                        # default path unchanged
-    model.fused_mlm_head = True
+    assert model.fused_mlm_head is True
     b = synth.make_batch(d, 2, seed=1)
     with abi_cases.dry_run() as calls:
         out = model(b["img"].bfloat16(), b["vis_pe"].bfloat16(), b["input_ids"], b["segment_ids"], b["input_mask"], b["masked_ids"], None,
@@ -343,19 +342,16 @@ def test_fused_mlm_head_marshalling_dry_run():
                     vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
         sum(l.float().sum() for l in out).backward()
     assert calls == ["vlpk_linear_fwd"] * 3 + ["vlpk_embed_fwd", "vlpk_mask_pack", "vlpk_encoder_fwd", "vlpk_decoder_ce_fwd", "vlpk_decoder_ce_bwd",
-                     "vlpk_encoder_bwd", "vlpk_f32_to_bf16", "vlpk_embed_bwd"] + ["vlpk_linear_bwd"] * 3
+                     "vlpk_encoder_bwd", "vlpk_f32_to_bf16", "vlpk_embed_bwd", "vlpk_embed_tables_bwd"] + ["vlpk_linear_bwd"] * 3
     assert model.last_prediction_scores.shape == (2, b["masked_pos"].shape[1], d.vocab)
     for n in ("cls.predictions.bias", "cls.predictions.transform.dense.weight", "bert.embeddings.word_embeddings.weight"):
         p = dict(model.named_parameters())[n]
         assert p.grad is not None and p.grad.shape == p.shape and p.grad.dtype == p.dtype, n
 
 
-def test_fused_table_grads_marshalling_dry_run(monkeypatch):
-    """Opt-in embedding-table gradient path (VLP_FUSED_TABLE_GRADS=1, csrc/tables.cu) under the CPU dry-run."""
+def test_table_grads_marshalling_dry_run():
+    """Embedding-table gradient kernels (csrc/tables.cu) under the CPU dry-run."""
     from tools import abi_cases
-    from vlp_b200 import ops
-    assert ops.FUSED_TABLE_GRADS is False                       # default path unchanged
-    monkeypatch.setattr(ops, "FUSED_TABLE_GRADS", True)
     d, cfg = _tiny_config()
     model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions).bfloat16().train()
     b = synth.make_batch(d, 2, seed=1)
@@ -414,27 +410,10 @@ def test_row_kernels_reject_misaligned_pointers_before_launching():
     assert lib.vlpk_ln_res_drop_fwd(4, 100, ok[0], ok[1], ok[2], ok[3], ok[4], ok[5], None, 0, None) < 0             # H % 8
 
 
-def test_wave_remainder_split_plan():
-    """VLPK_GEMM_TAIL_SPLIT experiment (csrc/gemm.cu plan_tail_split): which hot GEMMs would be split and where."""
-    split = _lib.lib().vlpk_debug_plan_tail_split
-    M = 64 * 123
-    # N = 768 dgrads: 93 pair-tiles on 74 pairs -> 24 row blocks (72 tiles) lead, 1 728 rows follow with 128-wide tiles
-    assert split(M, 768, 3072, 0, 1, 3, 256, 2, 1) == 24 * 256
-    assert split(M, 768, 768, 0, 1, 0, 256, 2, 1) == 24 * 256
-    # FFN-up / dU: 372 tiles = 5 rounds + 2 tiles -> 30 row blocks lead
-    assert split(M, 3072, 768, 0, 0, 1, 256, 2, 1) == 30 * 256
-    assert split(M, 3072, 768, 0, 1, 4, 256, 2, 1) == 30 * 256
-    # well-filled last rounds, weight gradients (split-K) and Philox epilogues are left alone
-    assert split(M, 2304, 768, 0, 0, 0, 256, 2, 1) == 0
-    assert split(M, 768, 768, 0, 0, 0, 192, 2, 1) == 0
-    assert split(768, 3072, M, 1, 1, 6, 256, 2, 5) == 0
-    assert split(6400, 2048, 2048, 0, 0, 2, 256, 2, 1) == 0
-
-
-def test_debug_options_are_named_and_default_off():
+def test_debug_options_are_named():
     lib = _lib.lib()
-    for name in (b"tail_split", b"wgrad_stream", b"mask_pack_warp"):
-        assert lib.vlpk_debug_set_option(name, 0) == 0
+    for v in (0, 1):
+        assert lib.vlpk_debug_set_option(b"wgrad_stream", v) == 0
     assert lib.vlpk_debug_set_option(b"no_such_option", 1) < 0 and b"unknown option" in lib.vlpk_last_error()
 
 

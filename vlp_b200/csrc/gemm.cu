@@ -628,61 +628,7 @@ int plan_gemm(const GemmDesc& g, int* bn_out, int* cg_out, int* splits_out) {
   return 0;
 }
 
-static int launch_gemm_one(const GemmDesc& g, cudaStream_t stream);
-
-// ---- experiment (VLPK_GEMM_TAIL_SPLIT=1, default off): wave-remainder split -----------------------------------------------
-// A persistent grid of S CTA(-pair)s runs T tiles in ceil(T/S) rounds; 93 tiles on 74 pairs (every N = 768 dgrad at B = 64) cost
-// two full rounds for 1.26 rounds of work.  When the last round would be less than half full, the row blocks that fit whole
-// rounds go to one launch with the planned tile and the remaining rows to a second launch with 128-wide tiles, which spread
-// over the machine at half the granularity (93 -> 72 big tiles + 42 small ones: ~1.55 instead of 2 rounds).  Same kernels,
-// same arithmetic per output element; only epilogues without a row-indexed Philox stream (no EPI_RELU) and no split-K.
-static int g_tail_split = -1;  // -1: take VLPK_GEMM_TAIL_SPLIT from the environment on first use
-void debug_set_tail_split(int on) { g_tail_split = on ? 1 : 0; }
-static bool tail_split_enabled() {
-  if (g_tail_split < 0) {
-    const char* e = getenv("VLPK_GEMM_TAIL_SPLIT");
-    g_tail_split = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return g_tail_split == 1;
-}
-
-// rows of the leading launch (0 = do not split)
-int plan_tail_split(const GemmDesc& g, int bn, int cg, int splits) {
-  if (g.a_mn || splits != 1 || g.epi == EPI_RELU || g.epi == EPI_REDUCE_F32 || g.bn != 0) return 0;
-  const int num_m = (g.M + BM * cg - 1) / (BM * cg);
-  const int num_n = (g.N + bn - 1) / bn;
-  const int slots = gemm_sms() / cg;
-  const long long tiles = static_cast<long long>(num_m) * num_n;
-  const long long rounds = (tiles + slots - 1) / slots;
-  if (rounds < 2) return 0;
-  const long long last = tiles - (rounds - 1) * slots;   // tiles in the last round
-  if (2 * last > slots) return 0;                        // more than half full: leave it
-  const int m_blocks = static_cast<int>(((rounds - 1) * slots) / num_n);  // whole row blocks that fit the full rounds
-  if (m_blocks <= 0 || m_blocks >= num_m) return 0;
-  return m_blocks * BM * cg;
-}
-
 int launch_gemm(const GemmDesc& g, cudaStream_t stream) {
-  if (!tail_split_enabled()) return launch_gemm_one(g, stream);
-  int bn = 128, cg = 1, splits = 1;
-  if (g.M <= 0 || g.N <= 0 || g.K <= 0 || plan_gemm(g, &bn, &cg, &splits) != 0) return launch_gemm_one(g, stream);  // let it report
-  const int m_lead = plan_tail_split(g, bn, cg, splits);
-  if (m_lead == 0) return launch_gemm_one(g, stream);
-  GemmDesc lead = g;
-  lead.M = m_lead;
-  lead.bn = bn;
-  VLPK_TRY(launch_gemm_one(lead, stream));
-  GemmDesc rest = g;
-  rest.M = g.M - m_lead;
-  rest.A = static_cast<const __nv_bfloat16*>(g.A) + static_cast<long long>(m_lead) * g.lda;
-  rest.D0 = static_cast<__nv_bfloat16*>(g.D0) + static_cast<long long>(m_lead) * g.ldd0;
-  if (g.D1 != nullptr) rest.D1 = static_cast<__nv_bfloat16*>(g.D1) + static_cast<long long>(m_lead) * g.ldd1;
-  if (g.aux != nullptr) rest.aux = g.aux + static_cast<long long>(m_lead) * g.ld_aux;
-  rest.bn = 128;
-  return launch_gemm_one(rest, stream);
-}
-
-static int launch_gemm_one(const GemmDesc& g, cudaStream_t stream) {
   VLPK_CHECK_ARG(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   VLPK_CHECK_ARG(g.N % 8 == 0, "gemm: N=%d must be a multiple of 8", g.N);
   VLPK_CHECK_ARG(g.nseg >= 1 && g.nseg <= 3, "gemm: nseg=%d", g.nseg);

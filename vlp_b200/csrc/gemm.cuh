@@ -50,8 +50,6 @@ struct GemmDesc {
 // Returns 0 on success, <0 on argument error, >0 cudaError_t.  Message via vlpk::set_error.
 int launch_gemm(const GemmDesc& g, cudaStream_t stream);
 void debug_set_cta_group(int cg);
-void debug_set_tail_split(int on);
 int plan_gemm(const GemmDesc& g, int* bn_out, int* cg_out, int* splits_out);
-int plan_tail_split(const GemmDesc& g, int bn, int cg, int splits);  // rows of the leading launch under VLPK_GEMM_TAIL_SPLIT (0 = none)
 
 }  // namespace vlpk

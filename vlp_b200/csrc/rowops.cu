@@ -499,23 +499,10 @@ __device__ __forceinline__ bool mask_attend<__nv_bfloat16>(__nv_bfloat16 v, int 
 template <>
 __device__ __forceinline__ bool mask_attend<long long>(long long v, int mode) { return v != 0; }
 
+// One warp per mask row: lane j tests elements j, j+32, j+64, j+96 (coalesced 256-byte requests for int64 masks) and the four
+// words come from __ballot_sync.  (Round 1 walked a whole 984-byte row per thread: 49 us for the [64,123,123] int64 mask.)
 template <typename T>
-__global__ void mask_pack_kernel(const T* m, long long sb, long long sr, int B, int rows, int kv, int mode, uint32_t* out) {
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<long long>(B) * rows) return;
-  const int b = static_cast<int>(idx / rows), r = static_cast<int>(idx % rows);
-  const T* p = m + b * sb + r * sr;
-  uint32_t w[4] = {0, 0, 0, 0};
-  for (int j = 0; j < kv; ++j)
-    if (mask_attend<T>(p[j], mode)) w[j >> 5] |= 1u << (j & 31);
-  reinterpret_cast<uint4*>(out)[idx] = make_uint4(w[0], w[1], w[2], w[3]);
-}
-
-// Experiment (option "mask_pack_warp", default off): one warp per mask row — lane j tests elements j, j+32, j+64, j+96 (coalesced
-// 256-byte requests for int64 masks) and the four words come from __ballot_sync, instead of one thread walking a whole row
-// (49 us for the [64,123,123] int64 mask of a training step in the round-1 profile; the row is 984 bytes).
-template <typename T>
-__global__ void __launch_bounds__(256) mask_pack_warp_kernel(const T* __restrict__ m, long long sb, long long sr, int B, int rows, int kv,
+__global__ void __launch_bounds__(256) mask_pack_kernel(const T* __restrict__ m, long long sb, long long sr, int B, int rows, int kv,
                                                               int mode, uint32_t* __restrict__ out) {
   const long long idx = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (idx >= static_cast<long long>(B) * rows) return;  // warp-uniform
@@ -532,36 +519,17 @@ __global__ void __launch_bounds__(256) mask_pack_warp_kernel(const T* __restrict
   if (lane == 0) reinterpret_cast<uint4*>(out)[idx] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-static int g_mask_pack_warp = -1;
-void set_mask_pack_warp(int on) { g_mask_pack_warp = on ? 1 : 0; }
-
 int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, long long stride_b, long long stride_r,
                      uint32_t* out, cudaStream_t s) {
   VLPK_CHECK_ARG(B > 0 && rows > 0 && kv > 0 && kv <= 128, "mask_pack: kv=%d must be in [1,128]", kv);
   VLPK_CHECK_ARG(!misaligned(out, 15), "mask_pack: the bitmask buffer must be 16-byte aligned");
   const long long n = static_cast<long long>(B) * rows;
-  if (g_mask_pack_warp < 0) {
-    const char* e = getenv("VLPK_MASK_PACK_WARP");
-    g_mask_pack_warp = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  if (g_mask_pack_warp == 1) {
-    const unsigned gridw = static_cast<unsigned>((n + 7) / 8);
-    LaunchScope scope(CAT_MISC, 0.0, s);
-    switch (dtype) {
-      case VLPK_DT_F32: mask_pack_warp_kernel<float><<<gridw, 256, 0, s>>>(static_cast<const float*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
-      case VLPK_DT_BF16: mask_pack_warp_kernel<__nv_bfloat16><<<gridw, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
-      case VLPK_DT_I64: mask_pack_warp_kernel<long long><<<gridw, 256, 0, s>>>(static_cast<const long long*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
-      default: set_error("mask_pack: unsupported dtype %d", dtype); return -1;
-    }
-    VLPK_CUDA(cudaGetLastError());
-    return 0;
-  }
-  const unsigned grid = static_cast<unsigned>((n + 127) / 128);
+  const unsigned gridw = static_cast<unsigned>((n + 7) / 8);
   LaunchScope scope(CAT_MISC, 0.0, s);
   switch (dtype) {
-    case VLPK_DT_F32: mask_pack_kernel<float><<<grid, 128, 0, s>>>(static_cast<const float*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
-    case VLPK_DT_BF16: mask_pack_kernel<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
-    case VLPK_DT_I64: mask_pack_kernel<long long><<<grid, 128, 0, s>>>(static_cast<const long long*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
+    case VLPK_DT_F32: mask_pack_kernel<float><<<gridw, 256, 0, s>>>(static_cast<const float*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
+    case VLPK_DT_BF16: mask_pack_kernel<__nv_bfloat16><<<gridw, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
+    case VLPK_DT_I64: mask_pack_kernel<long long><<<gridw, 256, 0, s>>>(static_cast<const long long*>(mask), stride_b, stride_r, B, rows, kv, mode, out); break;
     default: set_error("mask_pack: unsupported dtype %d", dtype); return -1;
   }
   VLPK_CUDA(cudaGetLastError());

@@ -61,7 +61,6 @@ int launch_embed_bwd(const EmbedArgs& a, cudaStream_t s);
 
 int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, long long stride_b, long long stride_r,
                      uint32_t* out, cudaStream_t s);
-void set_mask_pack_warp(int on);  // experiment toggle (see rowops.cu)
 int launch_colsum(const void* x, long long ld, long long M, int N, float* out, cudaStream_t s);
 int launch_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t s);
 

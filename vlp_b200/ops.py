@@ -28,9 +28,6 @@ def set_device_seed_tensor(t):
     _seed_dev = t
 
 
-# opt-in (not yet run on a B200): embedding-table gradients by vlpk_embed_tables_bwd instead of torch index_add_ (csrc/tables.cu)
-FUSED_TABLE_GRADS = os.environ.get("VLP_FUSED_TABLE_GRADS", "0") == "1"
-
 _encoder_grad_hook = None  # data parallelism: callable(flat_gradient_arena) invoked by EncoderStackFn.backward (vlp_b200/dp.py)
 
 
@@ -333,38 +330,22 @@ class EmbedFn(torch.autograd.Function):
                tabs[2].data_ptr(), L.ptr(visc), L.ptr(vpec), tabs[3].data_ptr(), stats.data_ptr(), dyc.data_ptr(), dz.data_ptr(), dg.data_ptr(),
                db.data_ptr(), drop, 1 << 20, L.stream())
         d_vis = dz[:, 1:R + 1] if vis_input else None
-        if FUSED_TABLE_GRADS:                                  # opt-in: one library call instead of the torch scatter below
-            V, P, T = tabs[0].shape[0], tabs[1].shape[0], tabs[2].shape[0]
-            d_word = torch.empty(V, H, device=dev, dtype=BF16)
-            scratch = torch.empty(V, H, device=dev, dtype=torch.float32)
-            d_pos = torch.zeros(P, H, device=dev, dtype=torch.float32)
-            d_type = torch.zeros(T, H, device=dev, dtype=torch.float32)
-            L.call("vlpk_embed_tables_bwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), dz.data_ptr(), V, P, T,
-                   d_word.data_ptr(), scratch.data_ptr(), d_pos.data_ptr(), d_type.data_ptr(), L.stream())
-            out = [None if d_vis is None else d_vis.to(dts[0]), None if d_vis is None else d_vis.to(dts[1]), d_word.to(dts[2]), d_pos.to(dts[3]),
-                   d_type.to(dts[4]), dg.to(dts[5]), db.to(dts[6])]
-            return tuple(out) + (None,) * 7
-        # scatter of the pre-LN gradient: region rows go to the projections, the other rows to the tables
-        if vis_input:
-            keep = torch.cat((torch.zeros(1, dtype=torch.long, device=dev), torch.arange(R + 1, Lq, device=dev)))
-            dz_tab = dz[:, keep].reshape(-1, H).float()
-            ids_tab = ids[:, keep].reshape(-1)
-            pos_tab = (pos[:, keep] if pos is not None else keep.unsqueeze(0).expand(B, -1)).reshape(-1)
-        else:
-            dz_tab = dz.reshape(-1, H).float()
-            ids_tab = ids.reshape(-1)
-            pos_tab = (pos if pos is not None else torch.arange(Lq, device=dev).unsqueeze(0).expand(B, -1)).reshape(-1)
-        d_word = torch.zeros(tabs[0].shape, device=dev, dtype=torch.float32).index_add_(0, ids_tab, dz_tab)
-        d_pos = torch.zeros(tabs[1].shape, device=dev, dtype=torch.float32).index_add_(0, pos_tab, dz_tab)
-        tt_all = (tt if tt is not None else torch.zeros_like(ids)).reshape(-1)
-        d_type = torch.zeros(tabs[2].shape, device=dev, dtype=torch.float32).index_add_(0, tt_all, dz.reshape(-1, H).float())
+        # pre-LN gradient -> tables: region rows feed the projections, the B x (L - R) looked-up rows are scattered by
+        # vlpk_embed_tables_bwd (csrc/tables.cu: touched-rows-only word/position scatter, segmented token-type sums)
+        V, P, T = tabs[0].shape[0], tabs[1].shape[0], tabs[2].shape[0]
+        d_word = torch.empty(V, H, device=dev, dtype=BF16)
+        scratch = torch.empty(V, H, device=dev, dtype=torch.float32)
+        d_pos = torch.zeros(P, H, device=dev, dtype=torch.float32)
+        d_type = torch.zeros(T, H, device=dev, dtype=torch.float32)
+        L.call("vlpk_embed_tables_bwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), dz.data_ptr(), V, P, T,
+               d_word.data_ptr(), scratch.data_ptr(), d_pos.data_ptr(), d_type.data_ptr(), L.stream())
         out = [None if d_vis is None else d_vis.to(dts[0]), None if d_vis is None else d_vis.to(dts[1]), d_word.to(dts[2]), d_pos.to(dts[3]),
                d_type.to(dts[4]), dg.to(dts[5]), db.to(dts[6])]
         return tuple(out) + (None,) * 7
 
 
 # ------------------------------------------------------------------------------------------------
-# masked-LM head tail: tied decoder + bias + per-position cross-entropy (opt-in)
+# masked-LM head tail: tied decoder + bias + per-position cross-entropy
 # ------------------------------------------------------------------------------------------------
 class DecoderCEFn(torch.autograd.Function):
     """loss[r] = CE(h[r] W^T + bias, labels[r]) (modeling.py:478-482 + 1108-1109) without fp32 logits; also returns the bf16

@@ -521,7 +521,9 @@ class BertForPreTrainingLossMask(PreTrainedBertModel, _RegionProjections):
         self._build_region_projections(config, enable_butd)
         self._load_fc7(required=False)
         self.tasks = tasks
-        self.fused_mlm_head = os.environ.get("VLP_FUSED_HEAD", "0") == "1"
+        # decoder + bias + cross-entropy through vlpk_decoder_ce_fwd/bwd (csrc/head.cu).  False selects the torch evaluation of the
+        # same ops, kept only as the comparison arm of tests/test_fused_head_gpu.py.
+        self.fused_mlm_head = os.environ.get("VLP_FUSED_HEAD", "1") != "0"
         if tasks == "vqa2":
             self.ans_classifier = nn.Sequential(nn.Linear(config.hidden_size, config.hidden_size * 2), nn.ReLU(),
                                                 nn.Linear(config.hidden_size * 2, 3129))
@@ -569,7 +571,7 @@ class BertForPreTrainingLossMask(PreTrainedBertModel, _RegionProjections):
             masked_lm_loss = pooled_output.new(1).fill_(0).float()
         else:
             gathered = torch.gather(sequence_output, 1, masked_pos.unsqueeze(2).expand(-1, -1, sequence_output.size(-1)))
-            if self.fused_mlm_head:                          # opt-in (VLP_FUSED_HEAD=1): decoder + bias + CE in libvlpk, SURVEY.md §8f-3
+            if self.fused_mlm_head:                          # decoder + bias + CE in libvlpk, SURVEY.md §8f-3
                 pred = self.cls.predictions
                 hid = pred.transform(gathered.to(pred.decoder.weight.dtype))
                 loss_flat, scores = ops.DecoderCEFn.apply(hid.reshape(-1, hid.size(-1)), pred.decoder.weight, pred.bias,
