@@ -262,6 +262,12 @@ int64_t vlpk_launch_count(void);
 /* utilities */
 int vlpk_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int vlpk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, void* stream);
+/* Test support: out[i] = 1 if element i of dropout site `site` is kept under `drop` (p, seed), else 0 — the decision every fused
+ * kernel takes through the same counter-based Philox function.  Element numbering per site: LayerNorm / embedding / Linear+ReLU
+ * sites: row * width + column; attention site: ((b * heads + h) * Lq + query) * 128 + key.  Sites: layer * 8 + {0 attention
+ * probabilities, 1 attention-output dropout, 2 FFN-output dropout}; 1<<20 embeddings; (1<<21)+{1 vis_embed, 2 vis_pe_embed}.
+ * n must be a multiple of 8. */
+int vlpk_debug_dropout_mask(const VlpkDropout* drop, uint64_t site, int64_t n, unsigned char* out, void* stream);
 int vlpk_add_bf16(void* dst, const void* a, const void* b, int64_t n, void* stream);
 
 /* Raw GEMM building block (exposed for tests / bring-up).  D[M,N] = sum_k A[m,k] B[n,k].

@@ -38,15 +38,28 @@ def linear(x, sd, prefix):
     return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
 
 
-def dropout(x, p, training):
-    return F.dropout(x, p, training) if (training and p > 0) else x
+# Optional keep-mask source for parity tests of the dropout-on (training) configuration: callable(site, shape) -> 0/1 tensor of
+# `shape` (or None).  `site` names the dropout call in the reference: ("vis_embed",) modeling.py:1007, ("vis_pe_embed",) :1018,
+# ("embed",) :240, ("attn", layer) :296, ("hid1", layer) :315, ("hid2", layer) :355.  With a provider the mask is applied exactly as
+# F.dropout would apply its own Bernoulli sample: x * keep / (1 - p).
+MASK_PROVIDER = None
+
+
+def dropout(x, p, training, site=None):
+    if not (training and p > 0):
+        return x
+    if MASK_PROVIDER is not None and site is not None:
+        keep = MASK_PROVIDER(site, tuple(x.shape))
+        if keep is not None:
+            return x * keep.to(x.dtype) / (1.0 - p)
+    return F.dropout(x, p, training)
 
 
 def region_projections(sd, vis_feats, vis_pe, p=0.0, training=False):
     """modeling.py:1003-1018 (definitions), :1035-1036 (application)."""
     v = torch.relu(linear(vis_feats, sd, "vis_embed.0"))
-    v = dropout(torch.relu(linear(v, sd, "vis_embed.2")), p, training)
-    pe = dropout(torch.relu(linear(vis_pe, sd, "vis_pe_embed.0")), p, training)
+    v = dropout(torch.relu(linear(v, sd, "vis_embed.2")), p, training, ("vis_embed",))
+    pe = dropout(torch.relu(linear(vis_pe, sd, "vis_pe_embed.0")), p, training, ("vis_pe_embed",))
     return v, pe
 
 
@@ -77,10 +90,10 @@ def embeddings(sd, vis, vpe, input_ids, token_type_ids=None, position_ids=None, 
         pos = torch.cat((pos[:, :1], vpe, pos[:, len_vis_input + 1:]), dim=1)
     tt = F.embedding(token_type_ids, sd[pre + "token_type_embeddings.weight"])
     e = layer_norm(w + pos + tt, sd[pre + "LayerNorm.weight"], sd[pre + "LayerNorm.bias"])
-    return dropout(e, p, training)
+    return dropout(e, p, training, ("embed",))
 
 
-def self_attention(sd, prefix, hidden, ext_mask, heads, history=None, p_attn=0.0, training=False):
+def self_attention(sd, prefix, hidden, ext_mask, heads, history=None, p_attn=0.0, training=False, layer=None):
     """modeling.py:268-303 — separate q/k/v Linears, scores/sqrt(d) + mask, softmax, dropout, P.V."""
     kv_in = hidden if history is None else torch.cat((history, hidden), dim=1)
     q = linear(hidden, sd, prefix + "query")
@@ -94,7 +107,7 @@ def self_attention(sd, prefix, hidden, ext_mask, heads, history=None, p_attn=0.0
 
     s = torch.matmul(split(q), split(k).transpose(-1, -2)) / math.sqrt(d)
     s = s + ext_mask
-    pr = dropout(torch.softmax(s, dim=-1), p_attn, training)
+    pr = dropout(torch.softmax(s, dim=-1), p_attn, training, None if layer is None else ("attn", layer))
     ctx = torch.matmul(pr, split(v))
     return ctx.permute(0, 2, 1, 3).contiguous().view(B, Lq, H)
 
@@ -102,11 +115,11 @@ def self_attention(sd, prefix, hidden, ext_mask, heads, history=None, p_attn=0.0
 def bert_layer(sd, i, hidden, ext_mask, heads, history=None, p_hidden=0.0, p_attn=0.0, training=False):
     """modeling.py:367-372 composing :326-330 (attention + self-output), :340-343, :353-357."""
     p = f"bert.encoder.layer.{i}."
-    ctx = self_attention(sd, p + "attention.self.", hidden, ext_mask, heads, history, p_attn, training)
-    a = dropout(linear(ctx, sd, p + "attention.output.dense"), p_hidden, training)
+    ctx = self_attention(sd, p + "attention.self.", hidden, ext_mask, heads, history, p_attn, training, layer=i)
+    a = dropout(linear(ctx, sd, p + "attention.output.dense"), p_hidden, training, ("hid1", i))
     a = layer_norm(a + hidden, sd[p + "attention.output.LayerNorm.weight"], sd[p + "attention.output.LayerNorm.bias"])
     h = gelu(linear(a, sd, p + "intermediate.dense"))
-    o = dropout(linear(h, sd, p + "output.dense"), p_hidden, training)
+    o = dropout(linear(h, sd, p + "output.dense"), p_hidden, training, ("hid2", i))
     return layer_norm(o + a, sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"])
 
 

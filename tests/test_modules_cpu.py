@@ -297,6 +297,22 @@ def test_bertadam_surface_matches_reference_contract():
     opt2 = opt_mod.BertAdam([{"params": [w], "weight_decay": 0.01}, {"params": [b, unused], "weight_decay": 0.0}], lr=1e-3, warmup=0.1, t_total=100)
     opt2.load_state_dict(sd)
     assert opt2.state[w]["step"] == 2 and torch.equal(opt2.state[w]["master"], opt.state[w]["master"])
+    # torch's base load_state_dict casts floating-point state to the parameter dtype (bf16 here): the override must hand the update
+    # kernel fp32 moments and an fp32 master copy again, bit-identical to what was saved
+    for key in ("next_m", "next_v", "master"):
+        t = opt2.state[w][key]
+        assert t.dtype == torch.float32 and t.is_contiguous() and torch.equal(t, opt.state[w][key]), key
+    assert "master" not in opt2.state[b] and opt2.state[b]["next_m"].dtype == torch.float32
+    with abi_cases.dry_run() as calls:
+        opt2.step()                                             # save -> load -> step round trip marshals cleanly
+    assert calls == ["vlpk_bertadam_step"] and opt2.state[w]["step"] == 3
+    opt2.state[w]["next_v"] = opt2.state[w]["next_v"].bfloat16()      # what the base class alone would have produced
+    with pytest.raises(RuntimeError, match="contiguous fp32"), abi_cases.dry_run():
+        opt2.step()
+    opt2.state[w]["next_v"] = opt2.state[w]["next_v"].float()
+    w.data.add_(1.0)                                            # weights changed behind the optimizer's back ...
+    opt2.resync_master()                                        # ... and re-adopted
+    assert torch.equal(opt2.state[w]["master"], w.detach().float())
 
 
 def test_bertadam_host_validation_in_the_library():

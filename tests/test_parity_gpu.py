@@ -76,6 +76,59 @@ def check_loss(got, ref):
     assert abs(got - ref) <= TOL_LOSS * max(1.0, abs(ref)), (got, ref)
 
 
+def compare_grads(model, ref, drift_fn=None, sample_idx_fn=None):
+    """Every parameter gradient of `model` against `ref[name]` = {"full": tensor} or a fingerprint {"sample": values[, "sample_idx"]}.
+    Criterion: rel-L2 <= 5e-2 and cosine >= 0.999; a tensor may exceed that flat bound only where the reference's
+    OWN fp32 -> bf16 drift on the same inputs (drift_fn() -> {name: rel-L2}) is itself above 2.5e-2 — i.e. where bf16 storage alone
+    already consumes the budget — and then must stay within 2x that drift.  Returns the worst rel-L2 seen; asserts with the list of
+    offending tensors."""
+    drift = None
+    worst, bad, relaxed = 0.0, [], []
+    for k, p in model.named_parameters():
+        fp = ref.get(k)
+        if fp is None:
+            continue
+        assert p.grad is not None, k
+        if k.endswith("attention.self.key.bias"):
+            # softmax is invariant to a per-query constant, so d(loss)/d(key.bias) is exactly 0 in exact arithmetic: the
+            # reference holds fp32 round-off (~1e-9), here it is bf16 round-off.  Compare against the scale of the
+            # sibling query.bias gradient instead of a relative error on noise.
+            sfp = ref[k.replace("key.bias", "query.bias")]
+            sib = float(sfp["full"].norm()) if "full" in sfp else float(sfp["norm"])
+            own = float(fp["full"].norm()) if "full" in fp else float(fp["norm"])
+            assert own < 1e-3 * sib
+            assert p.grad.float().norm().item() < 5e-2 * sib + 1e-6, (k, p.grad.float().norm().item(), sib)
+            continue
+        if "full" in fp:
+            refv = fp["full"]
+            if refv.norm() == 0:
+                assert float(p.grad.float().norm()) == 0.0, k
+                continue
+            r, c = rel(p.grad, refv), cosine(p.grad, refv)
+        else:
+            flat = p.grad.detach().float().cpu().flatten()
+            idx = fp["sample_idx"] if "sample_idx" in fp else sample_idx_fn(flat.numel())
+            got = flat[idx]
+            r, c = rel(got, fp["sample"]), cosine(got, fp["sample"])
+            if "norm" in fp and fp["norm"] > 0:
+                assert abs(float(flat.norm()) / fp["norm"] - 1.0) < TOL_GRAD, (k, float(flat.norm()), fp["norm"])
+        worst = max(worst, r)
+        if r < 0.0447 and c > 0.999:                       # flat criterion (cos >= 0.999 <=> rel <= 0.0447 for orthogonal error)
+            continue
+        if drift is None:
+            drift = drift_fn() if drift_fn is not None else {}
+        dk = drift.get(k, 0.0)
+        tol = 2.0 * dk if dk > 0.5 * TOL_GRAD else TOL_GRAD
+        if r < tol and c > 1.0 - tol * tol:
+            relaxed.append((k, round(r, 4), round(dk, 4)))
+        else:
+            bad.append((k, round(r, 4), round(c, 5), round(dk, 4)))
+    if relaxed:
+        print("gradients admitted through the 2x-reference-drift clause:", relaxed)
+    assert not bad, f"{len(bad)} gradient(s) out of tolerance: {bad[:12]}"
+    return worst
+
+
 @pytest.mark.parametrize("name", list(mg.CASES))
 def test_model_matches_reference_golden(name, golden_dir):
     """Forward activations, losses and every parameter gradient vs the UNMODIFIED reference's stored outputs."""
@@ -92,40 +145,7 @@ def test_model_matches_reference_golden(name, golden_dir):
     if tasks != "vqa2":
         assert rel(model.last_prediction_scores, gold["logits"]) < TOL_HID
     sum(l.sum() for l in losses).backward()
-    drift = None   # computed lazily: only needed when some gradient exceeds the flat tolerance
-    worst = 0.0
-    bad = []
-    for k, p in model.named_parameters():
-        fp = gold["grads"].get(k)
-        if fp is None:
-            continue
-        assert p.grad is not None, k
-        if k.endswith("attention.self.key.bias"):
-            # softmax is invariant to a per-query constant, so d(loss)/d(key.bias) is exactly 0 in exact arithmetic: the
-            # reference stores fp32 round-off (~1e-9), here it is bf16 round-off.  Compare against the scale of the
-            # sibling query.bias gradient instead of a relative error on noise.
-            sib = gold["grads"][k.replace("key.bias", "query.bias")]["full"].norm().item()
-            assert fp["full"].norm().item() < 1e-3 * sib
-            assert p.grad.float().norm().item() < 5e-2 * sib + 1e-6, (k, p.grad.float().norm().item(), sib)
-            continue
-        if "full" in fp:
-            ref = fp["full"]
-            if ref.norm() == 0:
-                assert float(p.grad.float().norm()) == 0.0, k
-                continue
-            r, c = rel(p.grad, ref), cosine(p.grad, ref)
-        else:
-            got = p.grad.detach().float().cpu().flatten()[fp["sample_idx"]]
-            r, c = rel(got, fp["sample"]), cosine(got, fp["sample"])
-        worst = max(worst, r)
-        if r < 0.0447 and c > 0.999:                       # flat criterion (cos >= 0.999 <=> rel <= 0.0447 for orthogonal error)
-            continue
-        if drift is None:
-            drift = reference_bf16_drift(name)
-        tol = max(TOL_GRAD, 2.0 * drift.get(k, 0.0))       # or: within 2x the reference's own fp32 -> bf16 drift
-        if not (r < tol and c > 1.0 - tol * tol):
-            bad.append((k, round(r, 4), round(c, 5), round(drift.get(k, 0.0), 4)))
-    assert not bad, f"{len(bad)} gradient(s) out of tolerance: {bad[:12]}"
+    worst = compare_grads(model, gold["grads"], drift_fn=lambda: reference_bf16_drift(name))
     # per-layer outputs (second forward with output_all_encoded_layers=True through BertModel)
     b = {k: v.cuda() for k, v in batch.items()}
     with torch.no_grad():
@@ -137,6 +157,30 @@ def test_model_matches_reference_golden(name, golden_dir):
         assert rel(got, ref) < TOL_HID
     assert rel(pooled, gold["pooled"]) < TOL_HID
     print(f"{name}: worst grad rel-L2 {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", list(mg.BIG_CASES))
+def test_full_size_matches_reference_golden(name, golden_dir):
+    """BASELINE.json configs[1] (12-layer BERT-base, B = 64, s2s) and configs[3] (VQA, B = 128, bidirectional) NUMERICALLY: losses,
+    samples of the last hidden state / MLM logits and every parameter gradient vs fingerprints of the unmodified reference's fp32
+    run at that size (oracle/make_golden.py BIG_CASES), with the reference's own bf16 drift stored beside them."""
+    dims, B, seed, mode, ragged, tasks = mg.BIG_CASES[name]
+    gold = torch.load(os.path.join(golden_dir, name + ".pt"))
+    batch = synth.make_batch(dims, B, seed=seed, mode=mode, ragged=ragged, tasks=tasks)
+    model = build(dims, tasks).eval()
+    cap = {}
+    model.bert.encoder.register_forward_hook(lambda m, i, o: cap.__setitem__("hidden", o[-1].detach().float().cpu().flatten()))
+    losses = run_model(model, batch, tasks)
+    for got, ref in zip(losses, gold["losses"]):
+        check_loss(got, ref)
+    hid = cap["hidden"]
+    assert rel(hid[mg.big_sample_idx(hid.numel(), 8192)], gold["hidden"]) < max(TOL_HID, 2.0 * gold["hidden_drift"])
+    if tasks != "vqa2":
+        lg = model.last_prediction_scores.detach().float().cpu().flatten()
+        assert rel(lg[mg.big_sample_idx(lg.numel(), 8192)], gold["logits"]) < TOL_HID
+    sum(l.sum() for l in losses).backward()
+    worst = compare_grads(model, gold["grads"], drift_fn=lambda: gold["drift"], sample_idx_fn=mg.big_sample_idx)
+    print(f"{name}: worst grad rel-L2 {worst:.3e} (reference bf16 drift: hidden {gold['hidden_drift']:.3e})")
 
 
 def test_fp32_parameter_model_is_supported():

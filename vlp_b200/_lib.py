@@ -107,6 +107,7 @@ _SIGS = {
     "vlpk_launch_count": (c_i64, []),
     "vlpk_f32_to_bf16": (c_int, [_P, _P, c_i64, _P]),
     "vlpk_colsum": (c_int, [_P, c_i64, c_i64, c_int, _P, _P]),
+    "vlpk_debug_dropout_mask": (c_int, [C.POINTER(VlpkDropout), c_u64, c_i64, _P, _P]),
     "vlpk_add_bf16": (c_int, [_P, _P, _P, c_i64, _P]),
     "vlpk_gemm": (c_int, [c_int, c_int, c_int, c_int, _P, c_i64, c_int, _P, c_i64, _P, _P, c_i64, _P, c_i64, _P, c_i64, c_int,
                           c_int, c_int, _P]),

@@ -661,6 +661,11 @@ int64_t vlpk_launch_count(void) { return launch_count(); }
 
 int vlpk_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) { return launch_f32_to_bf16(src, dst, n, S(stream)); }
 
+int vlpk_debug_dropout_mask(const VlpkDropout* drop, uint64_t site, int64_t n, unsigned char* out, void* stream) {
+  VLPK_CHECK_ARG(drop != nullptr && out != nullptr, "dropout_mask: null pointer");
+  return launch_dropout_mask(mk_drop(drop, drop->p, site), n, out, S(stream));
+}
+
 int vlpk_colsum(const void* x, int64_t ld, int64_t M, int N, float* out, void* stream) {
   VLPK_CHECK_ARG(x && out, "colsum: null pointer");
   return launch_colsum(x, ld, M, N, out, S(stream));

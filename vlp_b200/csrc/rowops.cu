@@ -584,6 +584,28 @@ int launch_colsum(const void* x, long long ld, long long M, int N, float* out, c
   return 0;
 }
 
+// Test support: the keep-decisions the kernels take for dropout site `site` under `seed`, element by element (1 = keep), produced by
+// the same dropout_keep8() every fused epilogue / row kernel calls — tests feed these masks to the fp32 oracle to check the
+// dropout-on (training) configuration numerically.
+__global__ void __launch_bounds__(256) dropout_mask_kernel(DropoutCfg d, long long n8, unsigned char* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint32_t keep = dropout_keep8(drop_seed(d), d.site, static_cast<uint64_t>(i), d.thresh16);
+  uint2 v;
+  v.x = (keep & 1u) | ((keep >> 1 & 1u) << 8) | ((keep >> 2 & 1u) << 16) | ((keep >> 3 & 1u) << 24);
+  v.y = (keep >> 4 & 1u) | ((keep >> 5 & 1u) << 8) | ((keep >> 6 & 1u) << 16) | ((keep >> 7 & 1u) << 24);
+  reinterpret_cast<uint2*>(out)[i] = v;
+}
+
+int launch_dropout_mask(const DropoutCfg& d, long long n, unsigned char* out, cudaStream_t s) {
+  VLPK_CHECK_ARG(n > 0 && n % 8 == 0 && !misaligned(out, 7), "dropout_mask: n=%lld must be a positive multiple of 8, out 8-byte aligned", n);
+  VLPK_CHECK_ARG(d.p > 0.f && d.p < 1.f, "dropout_mask: p=%g out of (0,1)", d.p);
+  const long long n8 = n / 8;
+  dropout_mask_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, s>>>(d, n8, out);
+  VLPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {

@@ -36,8 +36,22 @@ def set_encoder_grad_hook(fn):
     _encoder_grad_hook = fn
 
 
-def next_seed():
-    return (torch.initial_seed() * 1000003 + next(_seed_counter) * 7919) & 0x7FFFFFFFFFFFFFFF
+SEED_LOG = None  # tests: set to a list to record (kind, seed) of every dropout stream drawn (kind: "encoder", "linear:<site>", "embed")
+
+
+def next_seed(kind=None):
+    seed = (torch.initial_seed() * 1000003 + next(_seed_counter) * 7919) & 0x7FFFFFFFFFFFFFFF
+    if SEED_LOG is not None:
+        SEED_LOG.append((kind, seed))
+    return seed
+
+
+def dropout_keep_mask(p, seed, site, n):
+    """uint8 [n] keep decisions of dropout site `site` under `seed` (vlpk_debug_dropout_mask) — test support."""
+    n8 = (n + 7) // 8 * 8
+    out = torch.empty(n8, dtype=torch.uint8, device="cuda")
+    L.call("vlpk_debug_dropout_mask", _drop(p, seed), site, n8, out.data_ptr(), L.stream())
+    return out[:n]
 
 
 def _drop(p, seed):
@@ -161,7 +175,7 @@ class EncoderStackFn(torch.autograd.Function):
         acts = _Acts(n_layers, B, Lq, H, heads, I, x.device)
         shape = L.VlpkShape(B, Lq, Lq, H, heads, I)
         ws = _weight_structs(pk, n_layers)
-        seed = next_seed() if (training and (p_attn > 0 or p_hidden > 0)) else None
+        seed = next_seed("encoder") if (training and (p_attn > 0 or p_hidden > 0)) else None
         drop = _drop(max(p_attn, p_hidden), seed)
         L.call("vlpk_encoder_fwd", C.byref(shape), n_layers, ws, x.data_ptr(), mask_bits.data_ptr(), mask_bits.shape[1], acts.structs,
                float(p_attn if training else 0.0), float(p_hidden if training else 0.0), drop, L.stream())
@@ -262,7 +276,7 @@ class LinearActFn(torch.autograd.Function):
         bc = _bf16c(b)
         M = x2.shape[0]
         y = torch.empty(M, N, device=x.device, dtype=BF16)
-        seed = next_seed() if (training and p > 0 and act == 1) else None
+        seed = next_seed(f"linear:{site}") if (training and p > 0 and act == 1) else None
         drop = _drop(p, seed)
         L.call("vlpk_linear_fwd", M, N, Kp, x2.data_ptr(), Kp, wc.data_ptr(), Kp, L.ptr(bc), y.data_ptr(), N, act, drop, site, L.stream())
         ctx.save_for_backward(x2, wc, y)
@@ -304,7 +318,7 @@ class EmbedFn(torch.autograd.Function):
         pos = None if pos is None else pos.contiguous()
         y = torch.empty(B, Lq, H, device=ids.device, dtype=BF16)
         stats = torch.empty(B * Lq, 2, device=ids.device, dtype=torch.float32)
-        seed = next_seed() if (training and p > 0) else None
+        seed = next_seed("embed") if (training and p > 0) else None
         drop = _drop(p, seed)
         L.call("vlpk_embed_fwd", B, Lq, H, R, 1 if vis_input else 0, ids.data_ptr(), L.ptr(tt), L.ptr(pos), tabs[0].data_ptr(), tabs[1].data_ptr(),
                tabs[2].data_ptr(), L.ptr(visc), L.ptr(vpec), tabs[3].data_ptr(), tabs[4].data_ptr(), y.data_ptr(), stats.data_ptr(), drop, 1 << 20,

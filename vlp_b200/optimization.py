@@ -98,6 +98,44 @@ class BertAdam(Optimizer):
             state['master'] = p.detach().float().contiguous()
         return state
 
+    _FP32_STATE = ('next_m', 'next_v', 'master')
+
+    def load_state_dict(self, state_dict):
+        """torch's Optimizer.load_state_dict casts every floating-point state tensor to the PARAMETER dtype: with bf16 parameters the
+        moments and the fp32 master copy would come back as bf16 (half the bytes the update kernel addresses, and the master's extra
+        precision lost).  The kernel's state is fp32 by contract, so the saved tensors are re-installed from the checkpoint itself
+        — fp32, contiguous, on the parameter's device — after the base class has rebuilt the param <-> state mapping.  A reference
+        checkpoint (fp32 moments, no master) loads the same way; its master copy is then created from the parameter on first use
+        (run_img2txt_dist.py:430-434 loads optimizer state after the model weights)."""
+        saved_groups = state_dict['param_groups']
+        saved_state = state_dict['state']
+        super(BertAdam, self).load_state_dict(state_dict)
+        ids = [i for g in saved_groups for i in g['params']]
+        params = [p for g in self.param_groups for p in g['params']]
+        for i, p in zip(ids, params):
+            src = saved_state.get(i)
+            if src is None:
+                continue
+            st = self.state[p]
+            for key in self._FP32_STATE:
+                if key in src and torch.is_tensor(src[key]):
+                    st[key] = src[key].detach().to(device=p.device, dtype=torch.float32).contiguous().clone()
+            if 'step' in st and torch.is_tensor(st['step']):
+                st['step'] = int(st['step'])
+            if p.dtype != torch.bfloat16:
+                st.pop('master', None)
+
+    @torch.no_grad()
+    def resync_master(self):
+        """Re-derive the fp32 master copies from the current bf16 parameters.  Call after the parameters were changed behind the
+        optimizer's back once training has started (model.load_state_dict of weights only, a parameter broadcast, manual
+        re-initialisation): step() writes the parameters from the master copy, which would otherwise undo that change."""
+        for group in self.param_groups:
+            for p in group['params']:
+                st = self.state.get(p)
+                if st and 'master' in st:
+                    st['master'].copy_(p.detach().float())
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -141,6 +179,10 @@ class BertAdam(Optimizer):
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             grads.append(g)
             master = state.get('master')
+            for key, t in (('next_m', state['next_m']), ('next_v', state['next_v']), ('master', master)):
+                if t is not None and not (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel() and t.device == p.device):
+                    raise RuntimeError(f"vlp_b200 BertAdam: state['{key}'] must be a contiguous fp32 tensor of the parameter's size on its "
+                                       f"device (got {t.dtype}, {tuple(t.shape)}, {t.device}); state loaded without BertAdam.load_state_dict?")
             tab[i] = (p.data_ptr(), g.data_ptr(), 0 if master is None else master.data_ptr(), state['next_m'].data_ptr(),
                       state['next_v'].data_ptr(), p.numel(), wd, _DT[p.dtype], _DT[g.dtype], 0)
         prefix = np.zeros(n + 1, dtype=np.int32)
