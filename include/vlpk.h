@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VLPK_VERSION 100
+#define VLPK_VERSION 101
 
 /* dtype tags for vlpk_mask_pack */
 #define VLPK_BF16 0
@@ -86,6 +86,10 @@ typedef struct VlpkLayerActs {
   float* stats1; /* [B*Lq, 2]  (mean, rstd) of attention.output.LayerNorm */
   float* stats2; /* [B*Lq, 2] */
   void* kv;      /* incremental decode only: [B*Lkv, 2H] key|value projections; else NULL */
+  /* Optional (NULL = attention backward re-evaluates Philox): packed keep-decisions of the attention-probability dropout, 1 bit per
+   * element (byte i = elements 8i..8i+7, numbering as in vlpk_debug_dropout_mask; 128 key slots per query row).  Written by the
+   * forward attention kernel, read by the backward one. */
+  unsigned char* drop_attn; /* [B*heads*Lq*16] */
 } VlpkLayerActs;
 
 /* Scratch for backward, shared by all layers (bf16). */
@@ -196,7 +200,8 @@ int vlpk_mha_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
  * inference only (no dropout, nothing saved for backward).  x: [B*Lq,H] new rows; x_kv = cat(history, x): [B*Lkv,H]. */
 int vlpk_mha_incr_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* mask_bits,
                       int mask_rows, VlpkLayerActs* a, uint64_t layer_id, void* stream);
-/* Host-only: bytes the caller must provide for a shape.  out3 = { all VlpkLayerActs buffers of ONE layer,
+/* Host-only: bytes the caller must provide for a shape.  out3 = { all VlpkLayerActs buffers of ONE layer (without the optional
+ * drop_attn keep-bytes: B*heads*Lq*16),
  * all VlpkBwdScratch buffers (shared by the layers), the fp32 VlpkLayerGrads accumulators of ONE layer }. */
 int vlpk_workspace_bytes(const VlpkShape* s, size_t* out3);
 

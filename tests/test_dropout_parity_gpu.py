@@ -78,5 +78,21 @@ def test_training_mode_dropout_matches_oracle_with_replayed_masks(dims, B, mode,
     ev = run_model(build(dims, tasks, drop=0.0).eval(), batch, tasks)
     assert abs(float(sum(l.float().sum() for l in ev)) - float(sum(l.float().sum() for l in losses))) > 1e-3
     ref_grads = {k: {"full": v.grad} for k, v in sd.items() if v.grad is not None}
-    worst = compare_grads(model, ref_grads, drift_fn=None)
+
+    def drift():
+        """the reference algorithm's own fp32 -> bf16 drift under the SAME masks (oracle re-run with bf16 weights and inputs)"""
+        lo = {k: v.detach().to(torch.bfloat16) for k, v in synth.make_state_dict(dims, 0, tasks).items()}
+        lo["cls.predictions.decoder.weight"] = lo["bert.embeddings.word_embeddings.weight"]
+        for v in lo.values():
+            v.requires_grad_(True)
+        lb = {k: (v.to(torch.bfloat16) if v.is_floating_point() else v) for k, v in batch.items()}
+        O.MASK_PROVIDER = _provider(seeds, dims, B)[0]
+        try:
+            ll = O.pretraining_loss(lo, dims, lb, tasks=tasks, p_hidden=P, p_attn=P, training=True)
+            sum(l.float().sum() for l in ll).backward()
+        finally:
+            O.MASK_PROVIDER = None
+        return {k: rel(lo[k].grad, g["full"]) for k, g in ref_grads.items() if lo[k].grad is not None and float(g["full"].norm()) > 0}
+
+    worst = compare_grads(model, ref_grads, drift_fn=drift)
     print(f"dropout parity {dims.hidden}H/{dims.layers}L B={B} {mode}/{tasks}: worst grad rel-L2 {worst:.3e}")

@@ -7,6 +7,6 @@ from tools import bringup
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", ["gemm_kk", "gemm_epi", "gemm_dgrad", "gemm_wgrad", "attn", "attn_common_mode", "rowops"])
+@pytest.mark.parametrize("case", ["gemm_kk", "gemm_epi", "gemm_dgrad", "gemm_wgrad", "attn", "attn_full", "attn_common_mode", "rowops"])
 def test_kernel_family(case):
     assert bringup.CASES[case]()

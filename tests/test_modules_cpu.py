@@ -65,7 +65,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in vlpk.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.lib().vlpk_version() == 100
+    assert _lib.lib().vlpk_version() == 101
 
 
 def test_install_shadows_reference_import_path():

@@ -214,6 +214,58 @@ def case_attn():
     return ok
 
 
+def case_attn_full():
+    """Production item count (B = 64 x 12 heads = 768 (sequence, head) items -> every persistent CTA walks 2-3 items) with per-sample
+    mixed seq2seq / bidirectional masks and ragged lengths; forward and backward against fp32 torch on the same bf16 inputs, then the
+    same with attention dropout 0.1, the keep-mask replayed from the kernels' Philox stream (vlpk_debug_dropout_mask)."""
+    from vlp_b200 import ops
+    ok = True
+    torch.manual_seed(12)
+    B, heads, Lq, H = 64, 12, 123, 768
+    qkv = torch.randn(B, Lq, 3 * H, device=DEV).to(BF)
+    mask = torch.zeros(B, Lq, Lq, device=DEV, dtype=torch.int64)
+    for b in range(B):
+        n_tok = 102 + 1 + int(torch.randint(8, 21, (1,)))
+        if b % 4 == 3:
+            mask[b, :, :n_tok] = 1
+        else:
+            mask[b, :, :102] = 1
+            mask[b, 102:n_tok, 102:n_tok] = torch.tril(torch.ones(n_tok - 102, n_tok - 102, device=DEV, dtype=torch.int64))
+    bits = _mask_bits(mask)
+    q, k, v = qkv[..., :H], qkv[..., H:2 * H], qkv[..., 2 * H:]
+
+    def heads_view(t):
+        return t.float().view(B, Lq, heads, 64).permute(0, 2, 1, 3)
+
+    for p_drop in (0.0, 0.1):
+        ctx = torch.zeros(B, Lq, H, device=DEV, dtype=BF)
+        lse = torch.zeros(B, heads, Lq, device=DEV)
+        seed, site = 4242, 5
+        drop = L.VlpkDropout(p_drop, seed, None) if p_drop > 0 else None
+        L.call("vlpk_attn_core_fwd", B, heads, Lq, Lq, q.data_ptr(), 3 * H, k.data_ptr(), v.data_ptr(), 3 * H, bits.data_ptr(), Lq,
+               ctx.data_ptr(), H, lse.data_ptr(), drop, site, L.stream())
+        dctx = torch.randn(B, Lq, H, device=DEV).to(BF)
+        dqkv = torch.zeros(B, Lq, 3 * H, device=DEV, dtype=BF)
+        L.call("vlpk_attn_core_bwd", B, heads, Lq, q.data_ptr(), k.data_ptr(), v.data_ptr(), 3 * H, bits.data_ptr(), Lq, ctx.data_ptr(),
+               dctx.data_ptr(), H, lse.data_ptr(), dqkv.data_ptr(), dqkv[..., H:].data_ptr(), dqkv[..., 2 * H:].data_ptr(), 3 * H, drop, site,
+               L.stream())
+        torch.cuda.synchronize()
+        qf, kf, vf = (heads_view(t).clone().requires_grad_(True) for t in (q, k, v))
+        s = qf @ kf.transpose(-1, -2) / 8.0 + (1.0 - mask[:, None].float()) * -10000.0
+        pr = torch.softmax(s, -1)
+        if p_drop > 0:
+            keep = ops.dropout_keep_mask(p_drop, seed, site, B * heads * Lq * 128).view(B, heads, Lq, 128)[..., :Lq].float()
+            pr = pr * keep / (1.0 - p_drop)
+        ref_ctx = (pr @ vf).permute(0, 2, 1, 3).reshape(B, Lq, H)
+        tag = f"p={p_drop}"
+        ok &= report(f"attn full fwd ctx {tag}", ctx, ref_ctx)
+        ok &= report(f"attn full fwd lse {tag}", lse, torch.logsumexp(s, -1), tol=1e-3)
+        ref_ctx.backward(dctx.float())
+        for nm, t, g in (("dq", dqkv[..., :H], qf.grad), ("dk", dqkv[..., H:2 * H], kf.grad), ("dv", dqkv[..., 2 * H:], vf.grad)):
+            ok &= report(f"attn full bwd {nm} {tag}", t, g.permute(0, 2, 1, 3).reshape(B, Lq, H), tol=3e-2)
+    return ok
+
+
 def case_attn_common_mode():
     """Numerical stress for the attention backward: keys / values / queries dominated by a component shared by all rows
     (VLP's 100 near-identical region rows at initialisation) and a gradient that enters at two rows only (the VQA head).
@@ -359,7 +411,7 @@ def _perf(extras):
 
 
 CASES = {"gemm_kk": case_gemm_kk, "gemm_epi": case_gemm_epi, "gemm_dgrad": case_gemm_dgrad, "gemm_wgrad": case_gemm_wgrad,
-         "attn": case_attn, "attn_common_mode": case_attn_common_mode, "rowops": case_rowops, "perf": case_perf}
+         "attn": case_attn, "attn_full": case_attn_full, "attn_common_mode": case_attn_common_mode, "rowops": case_rowops, "perf": case_perf}
 
 if __name__ == "__main__":
     if len(sys.argv) > 1:

@@ -26,7 +26,7 @@ class VlpkShape(C.Structure):
 
 WEIGHT_FIELDS = ["wq", "wk", "wv", "bq", "bk", "bv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g", "ln2_b"]
 GRAD_FIELDS = ["wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g", "ln2_b"]
-ACT_FIELDS = ["qkv", "ctx", "t1", "y1", "u", "hmid", "t2", "y", "lse", "stats1", "stats2", "kv"]
+ACT_FIELDS = ["qkv", "ctx", "t1", "y1", "u", "hmid", "t2", "y", "lse", "stats1", "stats2", "kv", "drop_attn"]
 SCRATCH_FIELDS = ["dz2", "dt2", "du", "dy1", "dz1", "dt1", "dctx", "dqkv", "dx"]
 
 

@@ -84,33 +84,42 @@ int wgrad_linear(int M, int N, int K, const void* dy, int64_t lddy, const void* 
   return launch_gemm(g, st);
 }
 
-// ---- weight-gradient GEMMs of the layer backward on a side stream (VLPK_WGRAD_STREAM=0 / option "wgrad_stream" disables) ----
-// Inside one layer the wgrad of a Linear and the dgrad of the same Linear only share their INPUT, so they may run concurrently.
-// Both are persistent one-CTA-per-SM kernels: issued on two streams, the CTAs of the second start on the SMs the first kernel's
-// partial last wave leaves idle (93 pair-tiles on 74 CTA pairs for the N = 768 shapes), instead of after its last tile.  Fork /
-// join with events (capturable in a CUDA graph); one process drives one GPU, so a single side stream per process is enough.
-struct WgradSide {
+// ---- side stream ------------------------------------------------------------------------------------------------------------
+// One process drives one GPU, so a single side stream per process is enough; fork / join with events (capturable in a CUDA graph).
+// Backward: the weight-gradient GEMM of each Linear runs behind its dgrad (VLPK_WGRAD_STREAM=0 / option "wgrad_stream" disables):
+// inside one layer the two only share their INPUT; both are persistent one-CTA-per-SM kernels, so the wgrad's CTAs start on the SMs
+// the dgrad's partial last wave leaves idle (93 pair-tiles on 74 CTA pairs for the N = 768 shapes) instead of after its last tile.
+// (A forward use — precomputing the dropout keep-bits of all sites on this stream while the GEMMs leave the integer pipes idle —
+// was measured on the B200 and dropped: attention gained 0.22 ms per step, but the LayerNorm kernels became slower reading bytes than
+// evaluating Philox, and the generator's CTAs contended with the issue-bound kernels: +0.08 ms net.)
+struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
   bool pending = false;
+  bool failed = false;
 };
 
 int g_wgrad_stream = -1;  // -1: take VLPK_WGRAD_STREAM from the environment on first use, default on (measured +1 % on the B200 step)
 
-WgradSide* wgrad_side() {
-  static WgradSide side;
+SideStream* side_stream() {
+  static SideStream side;
+  if (side.stream == nullptr && !side.failed) {
+    if (cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming) != cudaSuccess) {
+      side.stream = nullptr;
+      side.failed = true;
+    }
+  }
+  return side.stream != nullptr ? &side : nullptr;
+}
+
+SideStream* wgrad_side() {
   if (g_wgrad_stream < 0) {
     const char* e = getenv("VLPK_WGRAD_STREAM");
     g_wgrad_stream = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
-  if (g_wgrad_stream == 1 && side.stream == nullptr &&
-      (cudaStreamCreateWithFlags(&side.stream, cudaStreamNonBlocking) != cudaSuccess ||
-       cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming) != cudaSuccess ||
-       cudaEventCreateWithFlags(&side.join, cudaEventDisableTiming) != cudaSuccess)) {
-    side.stream = nullptr;
-    g_wgrad_stream = 0;
-  }
-  return g_wgrad_stream == 1 ? &side : nullptr;
+  return g_wgrad_stream == 1 ? side_stream() : nullptr;
 }
 
 // One Linear's backward: weight gradient + input gradient, which only share their inputs.  Default: wgrad then dgrad on `main`
@@ -119,7 +128,7 @@ WgradSide* wgrad_side() {
 // `main` issues next.  wgrad_join(main) must follow before the wgrad's inputs are overwritten.
 template <class WgradFn, class DgradFn>
 int linear_bwd_pair(cudaStream_t main, WgradFn&& wgrad, DgradFn&& dgrad) {
-  WgradSide* sd = wgrad_side();
+  SideStream* sd = wgrad_side();
   if (sd == nullptr) {
     VLPK_TRY(wgrad(main));
     return dgrad(main);
@@ -132,7 +141,7 @@ int linear_bwd_pair(cudaStream_t main, WgradFn&& wgrad, DgradFn&& dgrad) {
 }
 
 int wgrad_join(cudaStream_t main) {
-  WgradSide* sd = wgrad_side();
+  SideStream* sd = wgrad_side();
   if (sd == nullptr || !sd->pending) return 0;
   VLPK_CUDA(cudaEventRecord(sd->join, sd->stream));
   VLPK_CUDA(cudaStreamWaitEvent(main, sd->join, 0));
@@ -150,6 +159,7 @@ int mha_fwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   ad.mask_bits = bits; ad.mask_rows = mask_rows;
   ad.o = a->ctx; ad.ld_o = H; ad.lse = a->lse;
   ad.drop = mk_drop(drop, p_attn, site_of(layer_id, SITE_ATTN));
+  ad.keep_out = (ad.drop.p > 0.f) ? a->drop_attn : nullptr;   // forward stores its keep-decisions for backward
   if (!incr) {
     VLPK_CHECK_ARG(s->Lq == s->Lkv, "mha_fwd: Lq != Lkv requires x_kv");
     GemmDesc g;  // packed QKV projection: three [H,H] weights read in place as N-segments
@@ -276,6 +286,7 @@ int mha_bwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   ad.dq = ws->dqkv; ad.dk = static_cast<bf16*>(ws->dqkv) + H; ad.dv = static_cast<bf16*>(ws->dqkv) + 2 * H;
   ad.ld_dqkv = 3 * H;
   ad.drop = mk_drop(drop, p_attn, site_of(layer_id, SITE_ATTN));
+  if (ad.drop.p > 0.f) ad.drop.bits = a->drop_attn;   // forward's keep-decisions (NULL: re-evaluate Philox)
   ad.dbias = g->bqkv;   // d bqkv = column sums of dQ | dK | dV, folded inside the attention backward kernel
   VLPK_TRY(launch_attn_bwd(ad, st));
   // ---- QKV projection: dWqkv += dqkv^T x ; dx = dqkv Wqkv + dz1 (residual branch of LN1)

@@ -38,6 +38,7 @@ struct AttnArgs {
   long long ld_o;
   DropoutCfg drop;
   float* dbias;  // bwd, optional: [3 * heads * 64] fp32, += column sums of dQ | dK | dV (gradient of the q/k/v biases)
+  unsigned char* keep_out;  // fwd, optional: packed dropout keep-decisions, 16 bytes per (sequence, head, query row)
 };
 
 __device__ __forceinline__ void sw_write16(uint8_t* tile, int row, int chunk, uint4 v) {
@@ -56,21 +57,67 @@ __device__ __forceinline__ void score_chunk(const uint32_t (&r)[32], uint32_t mb
   }
 }
 
+// Fast variant for a 32-column chunk in which every row of the warp attends to every column and all columns exist (the image-region
+// prefix of VLP's sequences: 3 of the 4 chunks of every row, seq2seq or bidirectional): one multiply per element.
+__device__ __forceinline__ void score_chunk_plain(const uint32_t (&r)[32], float (&t)[32]) {
+  const float sc = 0.125f * LOG2E;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(r[j]) * sc;
+}
+// warp-uniform: may this chunk take the plain path?
+__device__ __forceinline__ bool chunk_is_plain(uint32_t mbits, int col0, int Lkv) {
+  return (col0 + 32 <= Lkv) && __all_sync(0xffffffffu, mbits == 0xFFFFFFFFu);
+}
+
+// keep-decisions of this thread's 64 key columns of one query row: two 32-bit words (bit j of word c = column c*32 + j)
+__device__ __forceinline__ void attn_keep_words(const DropoutCfg& d, uint64_t dseed, uint64_t row_elem0, int hf, uint32_t (&kw)[2]) {
+  kw[0] = kw[1] = 0xFFFFFFFFu;
+  if (d.p <= 0.f) return;
+  if (d.bits != nullptr) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(d.bits + ((row_elem0 + hf * 64) >> 3)));
+    kw[0] = v.x;
+    kw[1] = v.y;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) w |= dropout_keep8(dseed, d.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, d.thresh16) << (8 * g);
+      kw[c] = w;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// forward  (256 threads: warp w owns TMEM lane quadrant w & 3 and column half w >> 2; 2 CTAs per SM)
+// forward: persistent, warp-specialised.  Each CTA walks (sequence, head) items item = blockIdx.x, + gridDim.x, ...; two CTAs
+// per SM (99 KB smem, 256 TMEM columns each) hide each other's residual latencies.
+//   warps 0-7  softmax : warp w owns TMEM lane quadrant w & 3 (32 query rows) and key-column half w >> 2
+//   warp  8    control : one lane issues every TMA load and every tcgen05.mma and runs ahead of the softmax warps
+// TMEM: two 128-column buffers X[0], X[1]; item i uses X[i & 1] for S_i = Q K^T and, once every softmax thread has consumed S_i,
+// for O_i = P V (columns [0,64)).  Pipeline across items (i = item in flight in the softmax warps):
+//   control : ... S_{i+1} issued as soon as Q,K_{i+1} have landed and X[(i+1)&1] has been drained by epilogue(i-1) — i.e. in the
+//             MIDDLE of item i — so the softmax warps never wait for a QK^T;  Q,K_{i+1} are fetched the moment S_i has retired,
+//             V_{i+1} the moment P_i V_i has retired.
+//   softmax : wait S_i -> pass 1 (row max) -> epilogue(i-1) (O_{i-1} / rowsum -> bf16 -> TMA store; its P V retired long ago)
+//             -> pass 2 (exp, Philox dropout, P_i -> smem) -> arrive "P_i ready".
 // ------------------------------------------------------------------------------------------------
-static constexpr int ATT_THREADS = 256;
+static constexpr int ATT_SOFTMAX_THREADS = 256;
+static constexpr int ATT_THREADS = ATT_SOFTMAX_THREADS + 32;
 
 struct FwdSmem {
-  static constexpr int OFF_Q = 0;                 // also O staging
+  static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = TILE_B;
   static constexpr int OFF_V = 2 * TILE_B;
   static constexpr int OFF_P = 3 * TILE_B;        // 2 atoms x 16 KB
-  static constexpr int OFF_RED = 5 * TILE_B;      // float[4][128] partial row max / sums exchange
-  static constexpr int OFF_BAR = OFF_RED + 2048;
-  static constexpr int TOTAL = OFF_BAR + 64;
+  static constexpr int OFF_O = 5 * TILE_B;        // output staging for the TMA store
+  static constexpr int OFF_RED = 6 * TILE_B;      // float[6][128]: partial row max | bf16-sum | exact sum, per column half
+  static constexpr int OFF_BAR = OFF_RED + 6 * 128 * 4;
+  static constexpr int NUM_BARS = 10;
+  static constexpr int TOTAL = OFF_BAR + NUM_BARS * 8 + 16;
   static constexpr int DYN = TOTAL + 1024;
 };
+
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -79,32 +126,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
   uint8_t* sK = smem + FwdSmem::OFF_K;
   uint8_t* sV = smem + FwdSmem::OFF_V;
   uint8_t* sP = smem + FwdSmem::OFF_P;
-  float* s_red = reinterpret_cast<float*>(smem + FwdSmem::OFF_RED);
+  uint8_t* sO = smem + FwdSmem::OFF_O;
+  float* s_max = reinterpret_cast<float*>(smem + FwdSmem::OFF_RED);
+  float* s_rsum = s_max + 256;
+  float* s_lsum = s_max + 512;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FwdSmem::OFF_BAR);
-  uint64_t* bar_qk = &bars[0];
-  uint64_t* bar_v = &bars[1];
-  uint64_t* bar_s = &bars[2];
-  uint64_t* bar_o = &bars[3];
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[4]);
+  uint64_t* bar_qk = &bars[0];      // TMA: Q,K of the next item landed
+  uint64_t* bar_v = &bars[1];       // TMA: V landed
+  uint64_t* bar_s = &bars[2];       // [2] MMA: S in X[j] complete (also: Q,K buffers free)
+  uint64_t* bar_o = &bars[4];       // [2] MMA: O in X[j] complete (also: V and P buffers free)
+  uint64_t* bar_p = &bars[6];       // softmax (256 arrivals): P written, S fully consumed
+  uint64_t* bar_x = &bars[7];       // [2] softmax (256 arrivals): O read out of X[j] -> buffer free for the next S
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[9]);
 
   pdl_launch_dependents();
-  const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, hf = warp >> 2;
-  const int row = q4 * 32 + lane;
-  const uint64_t dseed = drop_seed(a.drop);
+  const int n_items = a.B * a.heads;
+  const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (tid == 0) {
     tma_prefetch_desc(&tm.q);
     tma_prefetch_desc(&tm.k);
     tma_prefetch_desc(&tm.v);
+    tma_prefetch_desc(&tm.o);
     mbar_init(bar_qk, 1);
     mbar_init(bar_v, 1);
-    mbar_init(bar_s, 1);
-    mbar_init(bar_o, 1);
+    mbar_init(&bar_s[0], 1);
+    mbar_init(&bar_s[1], 1);
+    mbar_init(&bar_o[0], 1);
+    mbar_init(&bar_o[1], 1);
+    mbar_init(bar_p, ATT_SOFTMAX_THREADS);
+    mbar_init(&bar_x[0], ATT_SOFTMAX_THREADS);
+    mbar_init(&bar_x[1], ATT_SOFTMAX_THREADS);
     fence_mbar_init();
   }
-  if (warp == 0) {
+  if (warp == 8) {
     __syncwarp();
     tmem_alloc<256>(tmem_slot);
   }
@@ -112,130 +168,193 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 128;
   pdl_wait();
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(bar_qk, 2 * TILE_B);
-    tma_load_3d(sQ, &tm.q, bar_qk, h * HD, 0, b);
-    tma_load_3d(sK, &tm.k, bar_qk, h * HD, 0, b);
-    mbar_arrive_expect_tx(bar_v, TILE_B);
-    tma_load_3d(sV, &tm.v, bar_v, h * HD, 0, b);
-    mbar_wait(bar_qk, 0);
-    tc_fence_after();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+  if (warp == 8) {
+    // ===================================== control warp ==========================================
+    if (lane == 0 && my_items > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
+      auto load_qk = [&](int it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / a.heads, h = item - b * a.heads;
+        mbar_arrive_expect_tx(bar_qk, 2 * TILE_B);
+        tma_load_3d(sQ, &tm.q, bar_qk, h * HD, 0, b);
+        tma_load_3d(sK, &tm.k, bar_qk, h * HD, 0, b);
+      };
+      auto load_v = [&](int it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / a.heads, h = item - b * a.heads;
+        mbar_arrive_expect_tx(bar_v, TILE_B);
+        tma_load_3d(sV, &tm.v, bar_v, h * HD, 0, b);
+      };
+      auto issue_s = [&](int it) {   // S_it = Q K^T into X[it & 1]
+        const int j = it & 1;
+        mbar_wait(bar_qk, it & 1);                        // Q,K of item `it` landed
+        mbar_wait(&bar_x[j], ((it >> 1) & 1) ^ 1);        // X[j] drained by epilogue(it - 2) (passes at once for it < 2)
+        tc_fence_after();
 #pragma unroll
-    for (int k = 0; k < HD / 16; ++k)
-      umma_f16(tS, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
-               umma_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-    umma_commit(bar_s);
-  }
-
-  // mask bits of this query row for this thread's 64 key columns
-  uint32_t mb[2];
-  {
-    const int mr = (a.mask_rows == 1) ? 0 : min(row, a.mask_rows - 1);
-    const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4 + hf * 2));
-    mb[0] = m2.x; mb[1] = m2.y;
-  }
-
-  mbar_wait(bar_s, 0);
-  __syncwarp();
-  tc_fence_after();
-  const uint32_t t_lane = static_cast<uint32_t>(q4 * 32) << 16;
-
-  // pass 1: partial row max over this thread's 64 columns (log2 domain), exchanged through shared memory
-  float tmax = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    float t[32];
-    tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
-    tmem_ld_wait();
-    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16(tmem + j * 128, umma_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                   umma_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&bar_s[j]);
+      };
+      load_qk(0);
+      load_v(0);
+      issue_s(0);
+      for (int it = 0; it < my_items; ++it) {
+        const int j = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        if (it + 1 < my_items) {
+          mbar_wait(&bar_s[j], ph);          // S_it retired: the Q,K buffers may be refilled
+          load_qk(it + 1);
+          issue_s(it + 1);
+        }
+        mbar_wait(bar_p, it & 1);            // P_it in shared memory, S_it consumed by every softmax thread
+        mbar_wait(bar_v, it & 1);
+        tc_fence_after();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, t[j]);
-  }
-  s_red[hf * 128 + row] = tmax;
-  __syncthreads();
-  tmax = fmaxf(s_red[row], s_red[128 + row]);   // Lkv >= 1 guarantees at least one finite column in half 0
-  __syncthreads();
-  // pass 2: exponentiate, partial row sum, dropout, write un-normalised P (bf16) as the A operand of P·V
-  float rsum = 0.f, lsum = 0.f;
-  const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + row) * TL;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    uint32_t r[32];
-    float t[32];
-    tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
-    tmem_ld_wait();
-    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t keep = 0xFFu;
-      if (a.drop.p > 0.f) keep = dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16);
-      uint32_t pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x0 = fast_ex2(t[g * 8 + 2 * j] - tmax), x1 = fast_ex2(t[g * 8 + 2 * j + 1] - tmax);
-        lsum += x0 + x1;                                       // exact sum -> logsumexp (backward recomputes P from it)
-        const float e0 = bf16_round(x0), e1 = bf16_round(x1);  // the tensor core sees bf16 P: normalise O by the sum of
-        rsum += e0 + e1;                                       // exactly those values
-        const float p0 = ((keep >> (2 * j)) & 1u) ? e0 * a.drop.scale : 0.f;
-        const float p1 = ((keep >> (2 * j + 1)) & 1u) ? e1 * a.drop.scale : 0.f;
-        pk[j] = pack_bf16x2(p0, p1);
+        for (int k = 0; k < TL / 16; ++k)
+          umma_f16(tmem + j * 128, umma_smem_desc_sw128(smem_u32(sP) + (k >> 2) * TILE_B + (k & 3) * 32, 16, 1024),
+                   umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+        umma_commit(&bar_o[j]);
+        if (it + 1 < my_items) {
+          mbar_wait(&bar_o[j], ph);          // P_it V_it retired: V (and P) may be overwritten
+          load_v(it + 1);
+        }
       }
-      sw_write16(sP + hf * TILE_B, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
     }
+  } else {
+    // ===================================== softmax warps =========================================
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const uint32_t t_lane = static_cast<uint32_t>(q4 * 32) << 16;
+    const uint64_t dseed = drop_seed(a.drop);
+    float inv_prev = 0.f;   // 1 / rowsum of the item whose epilogue is still pending
+    int b_prev = 0, h_prev = 0;
+
+    // O_{it} / rowsum -> bf16 -> staging -> TMA store; frees X[it & 1]
+    auto epilogue = [&](int it, int b, int h, float inv) {
+      const int j = it & 1;
+      mbar_wait(&bar_o[j], (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld32(tmem + j * 128 + t_lane + hf * 32, r);   // this thread's 32 of the 64 output columns
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&bar_x[j]);
+      if (tid == 0) tma_store_wait_read<0>();            // the previous item's store has finished reading the staging tile
+      softmax_bar_sync();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          pk[jj] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * jj]) * inv, __uint_as_float(r[g * 8 + 2 * jj + 1]) * inv);
+        sw_write16(sO, row, hf * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+      }
+      fence_proxy_async_smem();
+      softmax_bar_sync();
+      if (tid == 0) {
+        tma_store_3d(&tm.o, sO, h * HD, 0, b);
+        tma_store_commit();
+      }
+    };
+
+    for (int it = 0; it < my_items; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / a.heads, h = item - b * a.heads;
+      const int j = it & 1;
+      const uint32_t tS = tmem + j * 128;
+      uint32_t mb[2];
+      {
+        const int mr = (a.mask_rows == 1) ? 0 : min(row, a.mask_rows - 1);
+        const uint2 m2 = __ldg(reinterpret_cast<const uint2*>(a.mask_bits + (static_cast<size_t>(b) * a.mask_rows + mr) * 4 + hf * 2));
+        mb[0] = m2.x; mb[1] = m2.y;
+      }
+      mbar_wait(&bar_s[j], (it >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      // pass 1: partial row max over this thread's 64 columns (log2 domain), exchanged through shared memory
+      float tmax = -INFINITY;
+      uint32_t plain_m = 0;   // bit c: chunk c of this warp takes the plain path
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
+        const bool pl = chunk_is_plain(mb[c], hf * 64 + c * 32, a.Lkv);
+        plain_m |= (pl ? 1u : 0u) << c;
+        tmem_ld_wait();
+        if (pl) {
+          float m = __uint_as_float(r[0]);
+#pragma unroll
+          for (int jj = 1; jj < 32; ++jj) m = fmaxf(m, __uint_as_float(r[jj]));
+          tmax = fmaxf(tmax, m * (0.125f * LOG2E));          // the scale is positive: max commutes with it
+        } else {
+          float t[32];
+          score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) tmax = fmaxf(tmax, t[jj]);
+        }
+      }
+      s_max[hf * 128 + row] = tmax;
+      softmax_bar_sync();
+      tmax = fmaxf(s_max[row], s_max[128 + row]);   // Lkv >= 1 guarantees at least one finite column in half 0
+      // the previous item's output: its P V retired long ago; this also guarantees that P / V of item it-1 are no longer read
+      if (it > 0) epilogue(it - 1, b_prev, h_prev, inv_prev);
+      // pass 2: exponentiate, partial row sums, dropout, write un-normalised P (bf16) as the A operand of P V
+      float rsum = 0.f, lsum = 0.f;
+      const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + min(row, a.Lq - 1)) * TL;
+      uint32_t kw[2];
+      attn_keep_words(a.drop, dseed, row_elem0, hf, kw);
+      if (a.keep_out != nullptr && row < a.Lq) *reinterpret_cast<uint2*>(a.keep_out + ((row_elem0 + hf * 64) >> 3)) = make_uint2(kw[0], kw[1]);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        float t[32];
+        tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
+        tmem_ld_wait();
+        if ((plain_m >> c) & 1u) score_chunk_plain(r, t); else score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t keep = (kw[c] >> (8 * g)) & 0xFFu;
+          uint32_t pk[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float x0 = fast_ex2(t[g * 8 + 2 * jj] - tmax), x1 = fast_ex2(t[g * 8 + 2 * jj + 1] - tmax);
+            lsum += x0 + x1;                                       // exact sum -> logsumexp (backward recomputes P from it)
+            const float e0 = bf16_round(x0), e1 = bf16_round(x1);  // the tensor core sees bf16 P: normalise O by the sum of
+            rsum += e0 + e1;                                       // exactly those values
+            const float p0 = ((keep >> (2 * jj)) & 1u) ? e0 * a.drop.scale : 0.f;
+            const float p1 = ((keep >> (2 * jj + 1)) & 1u) ? e1 * a.drop.scale : 0.f;
+            pk[jj] = pack_bf16x2(p0, p1);
+          }
+          sw_write16(sP + hf * TILE_B, row, c * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(bar_p);
+      s_rsum[hf * 128 + row] = rsum;
+      s_lsum[hf * 128 + row] = lsum;
+      softmax_bar_sync();
+      rsum = s_rsum[row] + s_rsum[128 + row];
+      lsum = s_lsum[row] + s_lsum[128 + row];
+      if (hf == 0 && a.lse != nullptr && row < a.Lq)
+        a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] = (tmax + log2f(lsum)) * LN2;
+      inv_prev = 1.0f / rsum;
+      b_prev = b;
+      h_prev = h;
+    }
+    if (my_items > 0) epilogue(my_items - 1, b_prev, h_prev, inv_prev);
+    if (tid == 0) tma_store_wait<0>();
   }
-  s_red[hf * 128 + row] = rsum;
-  s_red[256 + hf * 128 + row] = lsum;
-  fence_proxy_async_smem();
+
   tc_fence_before();
   __syncthreads();
-  rsum = s_red[row] + s_red[128 + row];
-  lsum = s_red[256 + row] + s_red[384 + row];
-
-  if (tid == 0) {
-    mbar_wait(bar_v, 0);
-    tc_fence_after();
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
-#pragma unroll
-    for (int k = 0; k < TL / 16; ++k)
-      umma_f16(tO, umma_smem_desc_sw128(smem_u32(sP) + (k >> 2) * TILE_B + (k & 3) * 32, 16, 1024),
-               umma_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
-    umma_commit(bar_o);
-  }
-  if (hf == 0 && a.lse != nullptr && row < a.Lq)
-    a.lse[(static_cast<size_t>(b) * a.heads + h) * a.Lq + row] = (tmax + log2f(lsum)) * LN2;
-
-  mbar_wait(bar_o, 0);
-  __syncwarp();
   tc_fence_after();
-  const float inv = 1.0f / rsum;
-  {
-    uint32_t r[32];
-    tmem_ld32(tO + t_lane + hf * 32, r);   // this thread's 32 of the 64 output columns
-    tmem_ld_wait();
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      uint32_t pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        pk[j] = pack_bf16x2(__uint_as_float(r[g * 8 + 2 * j]) * inv, __uint_as_float(r[g * 8 + 2 * j + 1]) * inv);
-      sw_write16(sQ, row, hf * 4 + g, make_uint4(pk[0], pk[1], pk[2], pk[3]));  // Q tile is dead: reuse as staging
-    }
-  }
-  fence_proxy_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (tid == 0) {
-    tma_store_3d(&tm.o, sQ, h * HD, 0, b);
-    tma_store_commit();
-    tma_store_wait<0>();
-  }
-  tc_fence_after();
-  if (warp == 0) {
+  if (warp == 8) {
     __syncwarp();
     tmem_dealloc<256>(tmem);
   }
@@ -258,7 +377,9 @@ struct BwdSmem {
   static constexpr int DYN = TOTAL + 1024;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
+static constexpr int ATT_BWD_THREADS = 256;
+
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 2) attn_bwd_kernel(const __grid_constant__ AttnTmaps tm, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem + BwdSmem::OFF_Q;
@@ -336,29 +457,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
   __syncwarp();
   tc_fence_after();
   const uint32_t t_lane = static_cast<uint32_t>(q4 * 32) << 16;
-  const uint64_t row_elem0 = ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + row) * TL;
   // pass A: delta_r = sum_j P_rj dP_rj with the SAME recomputed P that pass B multiplies with, so that sum_j dS_rj = 0 holds
   // to fp32 round-off.  (The usual shortcut delta = dO . O inherits the bf16 rounding of O; when keys / values share a large
   // common component — VLP's 100 near-identical region rows at initialisation — that error is amplified by |mean| / |spread|
   // and reached 10-20 % in dQ/dK on the VQA parity case.)
   float delta = 0.f;
-  uint32_t kb0 = 0xFFFFFFFFu, kb1 = 0xFFFFFFFFu;  // dropout keep mask of this thread's 64 columns (Philox evaluated once)
+  uint32_t kw[2];  // dropout keep mask of this thread's 64 columns (forward's bytes when available, else Philox evaluated once)
+  attn_keep_words(a.drop, dseed, ((static_cast<uint64_t>(b) * a.heads + h) * a.Lq + min(row, a.Lq - 1)) * TL, hf, kw);
+  uint32_t plain_m = 0;
 #pragma unroll 1
   for (int c = 0; c < 2; ++c) {
     uint32_t r[32], d[32];
     float t[32];
     tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
     tmem_ld32(tdP + t_lane + hf * 64 + c * 32, d);
+    const bool pl = chunk_is_plain(mb[c], hf * 64 + c * 32, a.Lkv);
+    plain_m |= (pl ? 1u : 0u) << c;
     tmem_ld_wait();
-    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
-    uint32_t kbc = 0xFFFFFFFFu;
-    if (a.drop.p > 0.f) {
-      kbc = 0u;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        kbc |= dropout_keep8(dseed, a.drop.site, (row_elem0 + hf * 64 + c * 32 + g * 8) >> 3, a.drop.thresh16) << (8 * g);
-    }
-    if (c == 0) kb0 = kbc; else kb1 = kbc;
+    if (pl) score_chunk_plain(r, t); else score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+    const uint32_t kbc = kw[c];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const uint32_t keep = (kbc >> (8 * g)) & 0xFFu;
@@ -381,10 +498,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_bwd_kernel(const __grid_c
     tmem_ld32(tS + t_lane + hf * 64 + c * 32, r);
     tmem_ld32(tdP + t_lane + hf * 64 + c * 32, d);
     tmem_ld_wait();
-    score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
+    if ((plain_m >> c) & 1u) score_chunk_plain(r, t); else score_chunk(r, mb[c], hf * 64 + c * 32, a.Lkv, t);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const uint32_t keep = ((c == 0 ? kb0 : kb1) >> (8 * g)) & 0xFFu;
+      const uint32_t keep = (kw[c] >> (8 * g)) & 0xFFu;
       uint32_t pk[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -523,13 +640,16 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
   a.lse = d.lse; a.o_ptr = nullptr; a.do_ptr = nullptr; a.ld_o = d.ld_o;
   a.drop = d.drop;
   a.dbias = nullptr;
+  a.keep_out = d.keep_out;
   static bool attr_set = false;
   if (!attr_set) {
     VLPK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::DYN));
     attr_set = true;
   }
   LaunchScope scope(CAT_ATTN_FWD, 4.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
-  VLPK_CUDA(launch_ex(attn_fwd_kernel, dim3(d.heads, d.B), dim3(ATT_THREADS), FwdSmem::DYN, stream, 1, tm, a));
+  const int n_items = d.B * d.heads;
+  const int slots = 2 * num_sms();   // two CTAs per SM
+  VLPK_CUDA(launch_ex(attn_fwd_kernel, dim3(n_items < slots ? n_items : slots), dim3(ATT_THREADS), FwdSmem::DYN, stream, 1, tm, a));
   return 0;
 }
 
@@ -556,13 +676,14 @@ int launch_attn_bwd(const AttnDesc& d, cudaStream_t stream) {
   a.ld_o = d.ld_o;
   a.drop = d.drop;
   a.dbias = d.dbias;
+  a.keep_out = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     VLPK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::DYN));
     attr_set = true;
   }
   LaunchScope scope(CAT_ATTN_BWD, 10.0 * d.B * d.heads * d.Lq * d.Lkv * HD, stream);
-  VLPK_CUDA(launch_ex(attn_bwd_kernel, dim3(d.heads, d.B), dim3(ATT_THREADS), BwdSmem::DYN, stream, 1, tm, a));
+  VLPK_CUDA(launch_ex(attn_bwd_kernel, dim3(d.heads, d.B), dim3(ATT_BWD_THREADS), BwdSmem::DYN, stream, 1, tm, a));
   return 0;
 }
 

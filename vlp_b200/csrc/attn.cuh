@@ -17,7 +17,8 @@ struct AttnDesc {
   const uint32_t* mask_bits = nullptr;  // [B, mask_rows, 4] packed by vlpk_mask_pack
   int mask_rows = 0;                    // Lq or 1
   float* lse = nullptr;                 // [B, heads, Lq] (fwd: optional output ; bwd: input)
-  DropoutCfg drop = {0.f, 1.f, 0u, 0ull, 0ull, nullptr};
+  DropoutCfg drop = {0.f, 1.f, 0u, 0ull, 0ull, nullptr};   // backward: drop.bits = forward's keep_out (or null: re-evaluate Philox)
+  unsigned char* keep_out = nullptr;  // forward, optional: [B*heads*Lq*16] packed keep-decisions of the attention dropout
   // backward only
   const void* d_o = nullptr;  // [B, Lq, ld_o]
   void* dq = nullptr;

@@ -296,6 +296,8 @@ struct DropoutCfg {
   uint64_t seed;
   uint64_t site;  // distinguishes (layer, site) streams
   const unsigned long long* seed_ptr;  // optional device-side counter added to seed (CUDA-graph replays)
+  const unsigned char* bits;  // optional (attention backward): forward's keep-decisions of this site, bits[i] = dropout_keep8(seed,
+                              // site, i), read back instead of re-evaluating Philox (the kernel is instruction-issue bound)
 };
 
 __device__ __forceinline__ uint64_t drop_seed(const DropoutCfg& d) {
@@ -305,6 +307,7 @@ __device__ __forceinline__ uint64_t drop_seed(const DropoutCfg& d) {
 __host__ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t site,
                                         const unsigned long long* seed_ptr = nullptr) {
   DropoutCfg d;
+  d.bits = nullptr;
   d.seed_ptr = seed_ptr;
   d.p = p;
   d.scale = p > 0.f ? 1.0f / (1.0f - p) : 1.0f;

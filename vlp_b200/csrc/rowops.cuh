@@ -65,4 +65,5 @@ int launch_colsum(const void* x, long long ld, long long M, int N, float* out, c
 int launch_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t s);
 int launch_dropout_mask(const DropoutCfg& d, long long n, unsigned char* out, cudaStream_t s);
 
+
 }  // namespace vlpk

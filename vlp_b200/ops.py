@@ -121,7 +121,7 @@ def _grad_views(arena, H, I):
 class _Acts:
     """Per-layer activation buffers (one bf16 + one fp32 allocation for the whole stack)."""
 
-    def __init__(self, n_layers, B, Lq, H, heads, I, device, Lkv=None):
+    def __init__(self, n_layers, B, Lq, H, heads, I, device, Lkv=None, drop_bits=False):
         M = B * Lq
         self.bf_sizes = [("qkv", M * 3 * H), ("ctx", M * H), ("t1", M * H), ("y1", M * H), ("u", M * I), ("hmid", M * I), ("t2", M * H),
                          ("y", M * H)]
@@ -134,6 +134,9 @@ class _Acts:
         self.bf = torch.empty(n_layers, per_bf, device=device, dtype=BF16)
         self.f32 = torch.empty(n_layers, per_f, device=device, dtype=torch.float32)
         self.structs = (L.VlpkLayerActs * n_layers)()
+        # training with dropout: 1 bit per attention probability (128 key slots per query row), written by the forward attention
+        # kernel and re-read by the backward one instead of re-evaluating Philox
+        self.bits = torch.empty(n_layers, B * heads * Lq * 16, device=device, dtype=torch.uint8) if drop_bits else None
         self.y = []
         for i in range(n_layers):
             st = self.structs[i]
@@ -146,6 +149,9 @@ class _Acts:
                 off += sz
             if Lkv is None:
                 st.kv = None
+            st.drop_attn = None
+            if self.bits is not None:
+                st.drop_attn = self.bits[i].data_ptr()
             off = 0
             basef = self.f32[i]
             for name, sz in self.f_sizes:
@@ -172,10 +178,10 @@ class EncoderStackFn(torch.autograd.Function):
         x = _bf16c(hidden)
         B, Lq, H = x.shape
         pk = [_bf16c(p) for p in params]
-        acts = _Acts(n_layers, B, Lq, H, heads, I, x.device)
+        seed = next_seed("encoder") if (training and (p_attn > 0 or p_hidden > 0)) else None
+        acts = _Acts(n_layers, B, Lq, H, heads, I, x.device, drop_bits=seed is not None)
         shape = L.VlpkShape(B, Lq, Lq, H, heads, I)
         ws = _weight_structs(pk, n_layers)
-        seed = next_seed("encoder") if (training and (p_attn > 0 or p_hidden > 0)) else None
         drop = _drop(max(p_attn, p_hidden), seed)
         L.call("vlpk_encoder_fwd", C.byref(shape), n_layers, ws, x.data_ptr(), mask_bits.data_ptr(), mask_bits.shape[1], acts.structs,
                float(p_attn if training else 0.0), float(p_hidden if training else 0.0), drop, L.stream())
