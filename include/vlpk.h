@@ -124,6 +124,11 @@ int vlpk_debug_set_option(const char* name, int value);
 int vlpk_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, int64_t stride_b, int64_t stride_r,
                    uint32_t* out, void* stream);
 
+/* Input staging: the loader's self-attention mask (vlp/seq2seq_loader.py:291-301) synthesised on the device from
+ * three integers per sample instead of shipping [B,L,L] int64: len_a region tokens (same for the batch), len_b[b] text tokens,
+ * mode[b] (0 = bidirectional, 1 = seq2seq).  Output: the packed bitmask vlpk_mask_pack would produce from the loader's matrix. */
+int vlpk_mask_synth(const int32_t* len_b, const int32_t* mode, int len_a, int B, int L, uint32_t* out, void* stream);
+
 /* y[M,N] = dropout(act(x[M,K] w[N,K]^T + b)) — vis_embed / vis_pe_embed Linears (modeling.py:1003-1018, 1035-1036).
  * K need not be tile aligned but ldx/ldw (elements) must be multiples of 8. */
 int vlpk_linear_fwd(int M, int N, int K, const void* x, int64_t ldx, const void* w, int64_t ldw, const void* bias, void* y,

@@ -536,6 +536,42 @@ int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int
   return 0;
 }
 
+// Device-side synthesis of the loader's self-attention mask (vlp/seq2seq_loader.py:291-301), straight into the packed form: the
+// reference builds a [L,L] int64 matrix per sample on a CPU worker and ships 121 KB per sample to the GPU; here three integers per
+// sample do.  len_a = region tokens, len_b = text tokens, st = len_a + 2, en = len_a + len_b + 3 (= tokens incl. [CLS] / 2 x [SEP]):
+//   s2s : every row attends to columns [0, st); rows in [st, en) additionally to columns [st, row]   (causal over the text)
+//   bi  : every row attends to columns [0, en)
+__global__ void __launch_bounds__(256) mask_synth_kernel(const int* __restrict__ len_b, const int* __restrict__ mode, int len_a, int B, int L,
+                                                          uint32_t* __restrict__ out) {
+  const long long idx = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (idx >= static_cast<long long>(B) * L) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int b = static_cast<int>(idx / L), r = static_cast<int>(idx % L);
+  const int st = len_a + 2, en = min(len_a + len_b[b] + 3, L);
+  const bool s2s = mode[b] != 0;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = lane + 32 * i;
+    bool on;
+    if (s2s) on = (j < st) || (r >= st && r < en && j >= st && j <= r);
+    else on = j < en;
+    w[i] = __ballot_sync(0xffffffffu, on && j < L);
+  }
+  if (lane == 0) reinterpret_cast<uint4*>(out)[idx] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+int launch_mask_synth(const int* len_b, const int* mode, int len_a, int B, int L, uint32_t* out, cudaStream_t s) {
+  VLPK_CHECK_ARG(len_b != nullptr && mode != nullptr && out != nullptr, "mask_synth: null pointer");
+  VLPK_CHECK_ARG(B > 0 && L > 0 && L <= 128 && len_a >= 0 && len_a + 3 <= L, "mask_synth: B=%d L=%d len_a=%d", B, L, len_a);
+  VLPK_CHECK_ARG(!misaligned(out, 15), "mask_synth: the bitmask buffer must be 16-byte aligned");
+  const long long n = static_cast<long long>(B) * L;
+  LaunchScope scope(CAT_MISC, 0.0, s);
+  mask_synth_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, 0, s>>>(len_b, mode, len_a, B, L, out);
+  VLPK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients) and fp32 -> bf16 conversion
 // ------------------------------------------------------------------------------------------------

@@ -61,6 +61,7 @@ int launch_embed_bwd(const EmbedArgs& a, cudaStream_t s);
 
 int launch_mask_pack(const void* mask, int dtype, int mode, int B, int rows, int kv, long long stride_b, long long stride_r,
                      uint32_t* out, cudaStream_t s);
+int launch_mask_synth(const int* len_b, const int* mode, int len_a, int B, int L, uint32_t* out, cudaStream_t s);
 int launch_colsum(const void* x, long long ld, long long M, int N, float* out, cudaStream_t s);
 int launch_f32_to_bf16(const float* x, void* y, long long n, cudaStream_t s);
 int launch_dropout_mask(const DropoutCfg& d, long long n, unsigned char* out, cudaStream_t s);

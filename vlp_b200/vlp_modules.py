@@ -431,6 +431,8 @@ class BertModel(PreTrainedBertModel):
         128-bit-per-row form the attention kernel consumes is attached to the returned tensor."""
         if attention_mask is None:
             attention_mask = torch.ones_like(input_ids)
+        if hasattr(attention_mask, "_vlpk_bits") and not torch.is_tensor(attention_mask):
+            return attention_mask            # staging.PackedAttentionMask: already in the kernels' packed form, nothing to extend
         if attention_mask.dim() == 2:
             m = attention_mask.unsqueeze(1).unsqueeze(2)
         elif attention_mask.dim() == 3:
