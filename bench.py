@@ -1,15 +1,21 @@
 """bench.py — VLP hot path throughput on B200 (driver contract: one JSON line on stdout from rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config caption|vqa|ccmix] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload = BASELINE.json configs[1]: BERT-base 12L/768H, 100 regions x 2048 + 20 tokens (L = 123), batch 64 per GPU,
-bf16, seq2seq mask, 3 masked positions, dropout 0.1 (the reference's training setting), forward + backward through
-BertForPreTrainingLossMask (+ NCCL gradient all-reduce when N > 1; weak scaling).  One step = one batch.
+Workloads (BASELINE.json `configs`), all BERT-base 12L/768H, 100 regions x 2048 + 20 tokens (L = 123), bf16, dropout 0.1 (the
+reference's training setting), forward + backward through BertForPreTrainingLossMask (+ NCCL gradient all-reduce when N > 1; weak
+scaling).  One step = one batch per GPU.
+  caption (default, configs[1] / [2]) : batch 64 per GPU, seq2seq mask, 3 masked positions
+  vqa     (configs[3])                : batch 128 per GPU, bidirectional mask, 3129-way answer head (tasks='vqa2')
+  ccmix   (configs[4])                : batch 64 per GPU, per-sample Bernoulli(0.75 seq2seq / 0.25 bidirectional) mask; run with
+                                        --steps 2000 for the sustained-throughput protocol (per-step p5 / p95, clock / power trace)
 
   value : samples/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.
-  e2e   : same metric through the public module API with HOST buffers: every step's 12-tensor batch is copied from pinned
-          host memory (double-buffered on a copy stream) and the loss is read back to the host, all inside the timed region.
+  e2e   : same metric through the product's staging API (vlp_b200.staging.BatchStager) with HOST buffers: every step's batch goes
+          pinned host memory -> device (bf16 features + 3 integers per sample for the mask, double-buffered on a copy stream) and the
+          loss is read back to the host, all inside the timed region (host wall clock).
+  optimizer : the same step including vlp_b200.optimization.BertAdam.step() (fused multi-tensor kernel), reported beside `value`.
   roofline : dominant kernel family (tcgen05 GEMM), algorithmic FLOPs / CUDA-event time of its launches inside one real step.
   cpu_baseline : the fp32 oracle port (same unfused eager op sequence as the reference) on the host cores, bounded sample.
 """
@@ -28,9 +34,17 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "image_text_samples_per_sec"
-WORKLOAD = ("BASELINE.json configs[1]: BERT-base 12L/768H/12 heads/3072, 100 regions x 2048-d + 20 text tokens (L=123), "
-            "batch 64 per GPU, seq2seq mask, 3 masked positions, dropout 0.1, fwd+bwd")
-PER_GPU_BATCH = 64
+CONFIGS = {
+    "caption": dict(batch=64, mode="s2s", tasks="img2txt",
+                    workload="BASELINE.json configs[1]: BERT-base 12L/768H/12 heads/3072, 100 regions x 2048-d + 20 text tokens (L=123), "
+                             "batch 64 per GPU, seq2seq mask, 3 masked positions, dropout 0.1, fwd+bwd"),
+    "vqa": dict(batch=128, mode="bi", tasks="vqa2",
+                workload="BASELINE.json configs[3]: VQA-2.0 shape, BERT-base, bidirectional mask + 3129-way answer head, 100 regions + 20 tokens "
+                         "(L=123), batch 128 per GPU, dropout 0.1, fwd+bwd"),
+    "ccmix": dict(batch=64, mode="mix", tasks="img2txt",
+                  workload="BASELINE.json configs[4]: CC-pretrain shape, BERT-base, per-sample mixed seq2seq (0.75) / bidirectional (0.25) mask, "
+                           "100 regions + 20 tokens (L=123), batch 64 per GPU, 3 masked positions, dropout 0.1, fwd+bwd"),
+}
 
 
 def load_peaks():
@@ -43,10 +57,10 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+    """Samples SM clock / power / throttle reasons through NVML while the timed region runs."""
 
     def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.power, self.reasons, self.max_mhz = [], [], set(), None
         self._stop = threading.Event()
         self._t = None
         try:
@@ -65,6 +79,7 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 for bit, name in names.items():
                     if r & bit:
@@ -85,24 +100,30 @@ class ClockSampler:
             self._t.join()
 
     def summary(self):
-        s = sorted(self.samples)
-        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s, p = sorted(self.samples), sorted(self.power)
+        out = {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        if s:
+            out.update({"sm_mhz_min": s[0], "sm_mhz_p5": s[len(s) // 20], "samples": len(s)})
+        if p:
+            out.update({"power_w_median": round(p[len(p) // 2], 1), "power_w_max": round(p[-1], 1)})
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port timed on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(batch=8, warmup=1, steps=2):
+def cpu_reference_run(config="caption", batch=8, warmup=1, steps=2):
     """fp32, eager, train mode, dropout 0.1 — the reference's own op sequence (oracle/vlp_oracle.py restates it op for op)."""
     from oracle import vlp_oracle as O
     from vlp_b200 import synth
+    cfg = CONFIGS[config]
     avail = os.cpu_count() or 1
     d = synth.BERT_BASE
-    sd = synth.make_state_dict(d, 0)
+    sd = synth.make_state_dict(d, 0, cfg["tasks"])
     for k, v in sd.items():
         if k != "cls.predictions.decoder.weight":
             v.requires_grad_(True)
-    b = synth.make_batch(d, batch, seed=1234)
+    b = synth.make_batch(d, batch, seed=1234, mode=cfg["mode"], tasks=cfg["tasks"])
     # "all the host threads it can use": eager PyTorch on small per-op tensors slows down when oversubscribed, so probe a few
     # thread counts on one forward pass and keep the fastest (the count actually used is reported as `cores`).
     cands = sorted({c for c in (8, 16, 32, 64, avail) if c <= avail})
@@ -110,9 +131,9 @@ def cpu_reference_run(batch=8, warmup=1, steps=2):
     for c in cands:
         torch.set_num_threads(c)
         with torch.no_grad():
-            O.pretraining_loss(sd, d, b)
+            O.pretraining_loss(sd, d, b, tasks=cfg["tasks"])
             t0 = time.perf_counter()
-            O.pretraining_loss(sd, d, b)
+            O.pretraining_loss(sd, d, b, tasks=cfg["tasks"])
             probe[c] = time.perf_counter() - t0
     cores = min(probe, key=probe.get)
     torch.set_num_threads(cores)
@@ -121,15 +142,15 @@ def cpu_reference_run(batch=8, warmup=1, steps=2):
         t0 = time.perf_counter()
         for v in sd.values():
             v.grad = None
-        loss = O.pretraining_loss(sd, d, b, p_hidden=0.1, p_attn=0.1, training=True)[0]
-        loss.backward()
+        losses = O.pretraining_loss(sd, d, b, tasks=cfg["tasks"], p_hidden=0.1, p_attn=0.1, training=True)
+        sum(l.sum() for l in losses).backward()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     per_step = sum(times) / len(times)
     return {"value": batch / per_step, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"oracle port (fp32 eager PyTorch, train mode, dropout 0.1), BERT-base L=123, batch {batch}, {warmup} warm-up + {steps} timed fwd+bwd steps; "
-                      f"{cores} of {avail} host threads (fastest of {cands} on a forward probe)",
+            "sample": f"oracle port (fp32 eager PyTorch, train mode, dropout 0.1), {config} shape, BERT-base L=123, batch {batch}, {warmup} warm-up + "
+                      f"{steps} timed fwd+bwd steps; {cores} of {avail} host threads (fastest of {cands} on a forward probe)",
             "s_per_step": per_step}
 
 
@@ -137,10 +158,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_run(batch=8, warmup=min(args.warmup, 1), steps=max(1, min(args.steps, 3)))
+    res = cpu_reference_run(args.config, batch=8, warmup=min(args.warmup, 1), steps=max(1, min(args.steps, 3)))
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: bounded sample, batch 8 per step"},
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config]["workload"], "note": "CPU arm: bounded sample, batch 8 per step"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -149,34 +171,31 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def build_model(device):
+def build_model(device, tasks):
     from vlp_b200 import synth
     from vlp_b200 import vlp_modules as vm
     d = synth.BERT_BASE
     cfg = vm.BertConfig(d.vocab, hidden_size=d.hidden, num_hidden_layers=d.layers, num_attention_heads=d.heads, intermediate_size=d.inter,
                         type_vocab_size=d.type_vocab, max_position_embeddings=d.max_pos, hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
     torch.manual_seed(0)
-    model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions, tasks="img2txt")
+    model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions, tasks=tasks)
     model = model.to(device=device, dtype=torch.bfloat16).train()
-    # bert.pooler.* never receives a gradient in img2txt training (SURVEY.md §7 "DDP unused parameters"); freezing it replaces the
-    # reference's find_unused_parameters=True graph walk.
-    for p in model.bert.pooler.parameters():
-        p.requires_grad_(False)
     return model, d
 
 
-BATCH_ORDER = ["input_ids", "segment_ids", "input_mask", "masked_ids", "masked_pos", "masked_weights", "is_next", "task_idx", "img",
-               "vis_masked_pos", "vis_pe", "ans_labels"]
-
-
-def step_fn(model, b):
+def step_fn(model, b, tasks):
     """The reference's training-loop body, run_img2txt_dist.py:479-483 + :575 (loss.backward())."""
-    loss_tuple = model(b["img"], b["vis_pe"], b["input_ids"], b["segment_ids"], b["input_mask"], b["masked_ids"], None, b["is_next"],
-                       masked_pos=b["masked_pos"], masked_weights=b["masked_weights"], task_idx=b["task_idx"],
-                       vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False, drop_worst_ratio=0.0)
+    loss_tuple = model(b["img"], b["vis_pe"], b["input_ids"], b["segment_ids"], b["input_mask"], b["masked_ids"],
+                       b["ans_labels"] if tasks == "vqa2" else None, b["is_next"], masked_pos=b["masked_pos"],
+                       masked_weights=b["masked_weights"], task_idx=b["task_idx"], vis_masked_pos=b["vis_masked_pos"], mask_image_regions=False,
+                       drop_worst_ratio=0.0)
     loss = loss_tuple[0] + loss_tuple[1] + loss_tuple[2]
     loss.backward()
     return loss
+
+
+def pct(sorted_vals, q):
+    return sorted_vals[min(len(sorted_vals) - 1, int(q * len(sorted_vals)))]
 
 
 def main():
@@ -185,15 +204,19 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vlp_b200")
+    ap.add_argument("--config", default="caption", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the optimizer-inclusive, exposed-communication and profile passes")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
 
     import torch.distributed as dist
     from vlp_b200 import _lib as L
-    from vlp_b200 import synth
+    from vlp_b200 import staging, synth
 
+    cfgw = CONFIGS[args.config]
+    tasks = cfgw["tasks"]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,30 +226,22 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    model, d = build_model(device)
+    model, d = build_model(device, tasks)
     net = model
     reducer = None
     if world > 1:
-        # backward runs in 4 groups of 3 layers; each group's gradients are one contiguous bf16 arena (42.5 MB) that is handed to
-        # NCCL (all-reduce AVG over NVLink) as soon as the group finishes, while the next group is still computing.
         if os.environ.get("VLP_BENCH_DP", "arena") == "torch_ddp":
             model.bert.encoder.layers_per_call = 3
             net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True, bucket_cap_mb=45,
-                                                            broadcast_buffers=False)
+                                                            broadcast_buffers=False, find_unused_parameters=True)
         else:
             from vlp_b200.dp import GradientAllReducer
-            reducer = GradientAllReducer(model, layers_per_call=3)
+            reducer = GradientAllReducer(model)
             reducer.broadcast_parameters(0)
-    B = PER_GPU_BATCH
-    host = synth.make_batch(d, B, seed=1234 + rank, mode="s2s")
+    B = cfgw["batch"]
+    host = synth.make_batch(d, B, seed=1234 + rank, mode=cfgw["mode"], tasks=tasks)
 
-    def to_dev(hb, non_blocking=False):
-        out = {}
-        for k in BATCH_ORDER:
-            out[k] = hb[k].to(device, non_blocking=non_blocking)
-        return out
-
-    dev_batch = to_dev(host)
+    dev_batch = {k: v.to(device) for k, v in host.items()}
     dev_batch["img"] = dev_batch["img"].bfloat16()
     dev_batch["vis_pe"] = dev_batch["vis_pe"].bfloat16()
 
@@ -234,17 +249,42 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def run_steps(n, get_batch, read_loss=None):
-        for i in range(n):
+    def one_step(batch, opt=None):
+        if opt is not None:
+            opt.zero_grad(set_to_none=True)
+        else:
             net.zero_grad(set_to_none=True)
-            loss = step_fn(net, get_batch(i))
-            if reducer is not None:
-                reducer.finish()
-            if read_loss is not None:
-                read_loss(i, loss)
+        loss = step_fn(net, batch, tasks)
+        if reducer is not None:
+            reducer.finish()
+        if opt is not None:
+            opt.step()
+        return loss
+
+    def timed_loop(n, opt=None):
+        """n steps on the device-resident batch; returns (total ms, sorted per-step ms) from one CUDA event per step."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.synchronize()
+        evs[0].record()
+        for i in range(n):
+            one_step(dev_batch, opt)
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        barrier()
+        per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(n))
+        return evs[0].elapsed_time(evs[n]), per
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
 
     # ---------------- device-resident timing ("value") ----------------
-    run_steps(warmup, lambda i: dev_batch)
+    for _ in range(warmup):
+        one_step(dev_batch)
     if world > 1:
         # after the all-reduce every rank must hold the same averaged gradients (ranks see different data shards)
         enc = model.bert.encoder.layer
@@ -254,82 +294,102 @@ def main():
         dist.all_gather(allc, chk)
         assert all(torch.equal(allc[0], c) for c in allc), f"gradients differ across ranks after all-reduce: {allc}"
 
-    torch.cuda.synchronize()
-    barrier()
     launches0 = L.lib().vlpk_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        torch.cuda.synchronize()
-        e0.record()
-        run_steps(args.steps, lambda i: dev_batch)
-        e1.record()
-        torch.cuda.synchronize()
-    barrier()
+        ms_total, per_step = timed_loop(args.steps)
     launches = L.lib().vlpk_launch_count() - launches0
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total / 1e3)
+    step_stats = {"mean_ms": ms_per_step, "p5_ms": max_over_ranks(pct(per_step, 0.05)), "p50_ms": max_over_ranks(pct(per_step, 0.50)),
+                  "p95_ms": max_over_ranks(pct(per_step, 0.95)),
+                  "first_tenth_mean_ms": None, "last_tenth_mean_ms": None}
 
-    # ---------------- end-to-end timing with host buffers ("e2e") ----------------
-    pinned = [{k: host[k].clone().pin_memory() for k in BATCH_ORDER} for _ in range(2)]
-    h2d_bytes = sum(pinned[0][k].numel() * pinned[0][k].element_size() for k in BATCH_ORDER)
-    copy_stream = torch.cuda.Stream()
-    loss_host = torch.zeros(args.steps + warmup, dtype=torch.float32).pin_memory()
-    slots = [None, None]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---------------- end-to-end timing with host buffers through the staging API ("e2e") ----------------
+    lb, md = staging.describe_mask(host["input_mask"], d.regions)
+    compact = {k: v for k, v in host.items() if k != "input_mask"}
+    compact["img"] = compact["img"].bfloat16()          # "bf16 feature files": the dataset-side conversion is not part of a step
+    compact["vis_pe"] = compact["vis_pe"].bfloat16()
+    compact["len_b"], compact["mode"] = lb, md
+    stager = staging.BatchStager(device, len_vis_input=d.regions, max_len=d.seq_len)
+    fields = {k: (tuple(v.shape), v.dtype) for k, v in compact.items()}
+    for _ in range(stager.depth):                       # fill the pinned slots once, as a loader writing into them would
+        slot = stager.slot(fields)
+        for k, v in compact.items():
+            slot[k].copy_(v)
+        stager.put(slot)
+        stager.get().done()
+    n_e2e = args.steps if args.steps <= 200 else 200
+    loss_host = torch.zeros(n_e2e + warmup, dtype=torch.float32).pin_memory()
 
-    def prefetch(i):
-        s = i & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[s])
-            slots[s] = to_dev(pinned[s], non_blocking=True)
-            ready[s].record(copy_stream)
-
-    def get_e2e_batch(i):
-        s = i & 1
-        torch.cuda.current_stream().wait_event(ready[s])
-        b = slots[s]
-        prefetch(i + 1)
-        return b
-
-    def read_loss(i, loss):
-        s = i & 1
-        consumed[s].record(torch.cuda.current_stream())
+    def e2e_step(i):
+        if i == 0:
+            stager.put(stager.slot(fields))
+        b = stager.get()
+        stager.put(stager.slot(fields))                 # next batch's copies overlap this step's compute
+        loss = one_step(b)
+        b.done()
         loss_host[i].copy_(loss.detach().float().reshape(()), non_blocking=True)
 
-    for ev in consumed:
-        ev.record(torch.cuda.current_stream())
-    prefetch(0)
-    run_steps(warmup, get_e2e_batch, read_loss)
+    for i in range(warmup):
+        e2e_step(i)
     torch.cuda.synchronize()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for i in range(warmup, warmup + args.steps):
-        net.zero_grad(set_to_none=True)
-        loss_i = step_fn(net, get_e2e_batch(i))
-        if reducer is not None:
-            reducer.finish()
-        read_loss(i, loss_i)
+    host_ms = []
+    for i in range(warmup, warmup + n_e2e):
+        th = time.perf_counter()
+        e2e_step(i)
+        host_ms.append((time.perf_counter() - th) * 1e3)
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    host_ms.sort()
     barrier()
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.steps / float(t_e2e)
-    final_loss = float(loss_host[warmup + args.steps - 1])
+    stager.get().done()                                  # drain the last prefetch
+    h2d_bytes = stager.h2d_bytes
+    e2e_value = B * world * n_e2e / t_e2e
+    final_loss = float(loss_host[warmup + n_e2e - 1])
+
+    # ---------------- optimizer-inclusive step, exposed communication ----------------
+    extras = {}
+    if not args.no_extras:
+        from vlp_b200.optimization import BertAdam
+        no_decay = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+                  {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]   # run_img2txt_dist.py:394-401
+        opt = BertAdam(groups, lr=3e-5, warmup=0.1, t_total=100000)
+        n_opt = min(args.steps, 30)
+        for _ in range(3):
+            one_step(dev_batch, opt)
+        ms_opt, _ = timed_loop(n_opt, opt)
+        ms_opt = max_over_ranks(ms_opt) / n_opt
+        extras["optimizer"] = {"value": B * world / (ms_opt / 1e3), "unit": "samples/s", "ms_per_step": ms_opt,
+                               "optimizer_ms": ms_opt - ms_per_step,
+                               "what": "fwd + bwd (+ all-reduce) + vlp_b200.optimization.BertAdam.step(): fused multi-tensor kernel, fp32 master "
+                                       "weights and moments, per-tensor clipping (optimization.py:112-182)"}
+        if reducer is not None:
+            reducer.enabled = False
+            for _ in range(2):
+                one_step(dev_batch)
+            ms_nocomm, _ = timed_loop(min(args.steps, 30))
+            reducer.enabled = True
+            ms_nocomm = max_over_ranks(ms_nocomm) / min(args.steps, 30)
+            extras["comm"] = {"exposed_ms_per_step": ms_per_step - ms_nocomm, "ms_per_step_without_allreduce": ms_nocomm,
+                              "how": "same loop with the gradient all-reduce switched off on every rank"}
 
     # ---------------- per-kernel-family profile of one real step (roofline) ----------------
     names = ["gemm_fwd", "gemm_dgrad", "gemm_wgrad", "attn_fwd", "attn_bwd", "ln_fwd", "ln_bwd", "embed", "misc"]
     prof = {}
     if rank == 0:
+        L.lib().vlpk_debug_set_option(b"wgrad_stream", 0)     # serialise the side-stream wgrads so that per-family event times do not overlap
+        for _ in range(2):
+            one_step(dev_batch)
         L.lib().vlpk_profile_reset()
         L.lib().vlpk_profile_enable(1)
-        run_steps(2, lambda i: dev_batch)
+        for _ in range(2):
+            one_step(dev_batch)
         torch.cuda.synchronize()
         L.lib().vlpk_profile_enable(0)
         for i, n in enumerate(names):
@@ -337,8 +397,10 @@ def main():
             L.lib().vlpk_profile_get(i, C.byref(a), C.byref(w), C.byref(c))
             prof[n] = {"ms_per_step": a.value / 2, "work_per_step": w.value / 2, "launches_per_step": c.value // 2}
         L.lib().vlpk_profile_reset()
+        L.lib().vlpk_debug_set_option(b"wgrad_stream", 1)
     else:
-        run_steps(2, lambda i: dev_batch)
+        for _ in range(4):
+            one_step(dev_batch)
         torch.cuda.synchronize()
     barrier()
 
@@ -348,39 +410,52 @@ def main():
         return
 
     peaks = load_peaks()
+    clk = clocks.summary()
     gemm_ms = sum(prof[n]["ms_per_step"] for n in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"))
     gemm_fl = sum(prof[n]["work_per_step"] for n in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"))
     gemm_n = sum(prof[n]["launches_per_step"] for n in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad"))
     achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    peak_tf = peaks["bf16_tflops_sustained"]
-    fl = synth.flops_per_sample()
+    # denominator: the burst cuBLAS figure unless this run itself was power-capped / clocked down (then the sustained one)
+    capped = ("sw_power_cap" in clk["reasons"]) or (clk["sm_mhz"] is not None and clk["sm_max_mhz"] and clk["sm_mhz"] < 0.95 * clk["sm_max_mhz"])
+    peak_tf = peaks["bf16_tflops_sustained"] if capped else peaks["bf16_tflops"]
+    fl = synth.flops_per_sample(tasks=tasks)
     step_tf = value / world * fl["total"] / 1e12
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(tp):
         tj = json.load(open(tp))
-        traffic, traffic_src = tj["gemm_dram_bytes_per_launch_avg"], tj["source"]
+        traffic, traffic_src = tj["gemm_dram_bytes_per_launch_avg"], "static: " + tj["source"]
     roofline = {"bound": "tensor", "kernel": "vlpk::gemm_kernel (tcgen05 GEMM family: fwd/dgrad/wgrad)", "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
+                "peak_source": f"MEASURED_PEAKS.json {'bf16_tflops_sustained' if capped else 'bf16_tflops (burst)'} ({peaks['source']}); "
+                               f"{'run was power-capped / clocked down' if capped else 'run stayed at full clocks, no power cap'}",
                 "launches_per_step": gemm_n, "flops_per_launch_avg": gemm_fl / max(gemm_n, 1), "avg_launch_us": gemm_ms * 1e3 / max(gemm_n, 1),
                 "gemm_share_of_step": gemm_ms / ms_per_step,
                 "whole_step": {"achieved": step_tf, "frac": step_tf / peak_tf, "flops_per_sample": fl["total"]},
                 "families_ms_per_step": {n: round(prof[n]["ms_per_step"], 4) for n in names},
+                "families_note": "CUDA events around every launch of one profiled step, side-stream overlap disabled for this pass",
                 "hbm_kernels": {n: {"GBps": (prof[n]["work_per_step"] / (prof[n]["ms_per_step"] * 1e-3) / 1e9 if prof[n]["ms_per_step"] > 0 else 0.0),
                                     "frac_of_hbm_peak": (prof[n]["work_per_step"] / (prof[n]["ms_per_step"] * 1e-3) / 1e9 / peaks["hbm_gbs"]
-                                                         if prof[n]["ms_per_step"] > 0 else 0.0)} for n in ("ln_fwd", "ln_bwd")}}
+                                                         if prof[n]["ms_per_step"] > 0 else 0.0)} for n in ("ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd")}}
+    n10 = max(1, args.steps // 10)
+    step_stats.pop("first_tenth_mean_ms"), step_stats.pop("last_tenth_mean_ms")
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "seq_len": d.seq_len, "parallelism": f"dp{world}" + ("" if world == 1 else (" torch-DDP" if reducer is None else " NCCL all-reduce of flat bf16 gradient arenas overlapped with backward")),
+            "config": {"workload": cfgw["workload"], "name": args.config, "global_batch": B * world, "seq_len": d.seq_len,
+                       "parallelism": f"dp{world}" + ("" if world == 1 else (" torch-DDP" if reducer is None else
+                                                                               " NCCL all-reduce of flat bf16 gradient arenas overlapped with backward")),
                        "l2": "per-step working set (2.3 GB saved activations + 0.23 GB weights) is far larger than the 126 MB L2; no explicit flush",
-                       "timing": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks"},
-            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                    "how": "pinned host batch (fp32 features + int64 ids/mask as the reference loader emits) -> double-buffered H2D on a copy stream -> "
-                           "BertForPreTrainingLossMask fwd+bwd -> loss copied to pinned host memory, host wall clock around the loop"},
-            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks.summary(), "final_loss": final_loss}
+                       "timing": "CUDA events on the launch stream (one per step), barrier + synchronize both sides, max over ranks"},
+            "step_ms": step_stats,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "steps": n_e2e,
+                    "host_enqueue_ms": {"p50": round(pct(host_ms, 0.5), 3), "p95": round(pct(host_ms, 0.95), 3), "max": round(host_ms[-1], 3)},
+                    "how": "vlp_b200.staging.BatchStager: pinned host batch (bf16 region features, int64 ids, 3 integers per sample for the mask) -> "
+                           "double-buffered H2D on a copy stream -> device-side mask synthesis -> BertForPreTrainingLossMask fwd+bwd -> loss copied to "
+                           "pinned host memory; host wall clock around the loop"},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clk, "final_loss": final_loss}
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
-        res = cpu_reference_run(batch=8, warmup=1, steps=2)
+        res = cpu_reference_run(args.config, batch=8, warmup=1, steps=2)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -95,7 +95,10 @@ def _reducer_worker(rank, world, port, q):
                             intermediate_size=d.inter, type_vocab_size=d.type_vocab, max_position_embeddings=d.max_pos)
         torch.manual_seed(rank)
         model = vm.BertForPreTrainingLossMask(cfg, enable_butd=True, len_vis_input=d.regions)
-        red = GradientAllReducer(model, layers_per_call=1)
+        enc = model.bert.encoder
+        before = (enc.layers_per_call, enc._vlpk_grad_hook)
+        red = GradientAllReducer(model, layer_groups=[1, 1])
+        assert enc.layers_per_call == [1, 1] and enc._vlpk_grad_hook == red._on_encoder_grads      # the hook belongs to THIS encoder
         red.broadcast_parameters(0)
         w0 = model.bert.encoder.layer[1].output.dense.weight.detach().clone()
         ref = w0.clone()
@@ -108,10 +111,22 @@ def _reducer_worker(rank, world, port, q):
         mean = (world + 1) / 2.0
         ok = torch.equal(w0, ref) and all(torch.allclose(p.grad, torch.full_like(p, mean)) for p in red.other) and \
             torch.allclose(arena, torch.full((1000,), mean))
+        # gradient accumulation: encoder gradients already populated when the arena arrives -> reduced values in place before return
+        enc.layer[0].output.dense.weight.grad = torch.zeros_like(enc.layer[0].output.dense.weight)
+        arena2 = torch.full((10,), float(rank + 1))
+        red._on_encoder_grads(arena2)
+        ok = ok and red._accumulating is True and torch.allclose(arena2, torch.full((10,), mean)) and not red._works
+        red.finish()
+        red.enabled = False                                     # switched off: nothing is touched
+        arena3 = torch.full((10,), float(rank + 1))
+        red._on_encoder_grads(arena3)
+        red.finish()
+        ok = ok and torch.equal(arena3, torch.full((10,), float(rank + 1)))
         enc_ids = {id(p) for p in model.bert.encoder.parameters()}
         disjoint = all(id(p) not in enc_ids for p in red.other)
         red.close()
-        q.put((rank, bool(ok), disjoint, model.bert.encoder.layers_per_call))
+        ok = ok and (enc.layers_per_call, enc._vlpk_grad_hook) == before           # close() restores the encoder
+        q.put((rank, bool(ok), disjoint, 1))
     finally:
         dist.destroy_process_group()
 

@@ -28,14 +28,6 @@ def set_device_seed_tensor(t):
     _seed_dev = t
 
 
-_encoder_grad_hook = None  # data parallelism: callable(flat_gradient_arena) invoked by EncoderStackFn.backward (vlp_b200/dp.py)
-
-
-def set_encoder_grad_hook(fn):
-    global _encoder_grad_hook
-    _encoder_grad_hook = fn
-
-
 SEED_LOG = None  # tests: set to a list to record (kind, seed) of every dropout stream drawn (kind: "encoder", "linear:<site>", "embed")
 
 
@@ -172,7 +164,7 @@ class EncoderStackFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, hidden, mask_bits, cfg, *params):
-        n_layers, heads, I, p_attn, p_hidden, training = cfg
+        n_layers, heads, I, p_attn, p_hidden, training = cfg[:6]
         _require_cuda(hidden, "hidden_states")
         ctx.set_materialize_grads(False)   # unused layer outputs must arrive as None in backward, not as zero tensors
         x = _bf16c(hidden)
@@ -193,11 +185,17 @@ class EncoderStackFn(torch.autograd.Function):
         ctx.pk = pk
         ctx.param_dtypes = [p.dtype for p in params]
         ctx.mark_non_differentiable(mask_bits)
-        return tuple(acts.y)
+        outs = tuple(acts.y)
+        acts.y = None        # ctx keeps the buffers (acts.bf / raw pointers), not the returned tensor objects: no output -> grad_fn -> ctx ->
+        return outs          # output reference cycle, so an un-backpropagated training forward is freed by reference counting
 
     @staticmethod
     def backward(ctx, *dys):
-        n_layers, heads, I, p_attn, p_hidden, training = ctx.cfg
+        n_layers, heads, I, p_attn, p_hidden, training = ctx.cfg[:6]
+        grad_hook = ctx.cfg[6] if len(ctx.cfg) > 6 else None      # data parallelism: callable(flat gradient arena) of the owning BertEncoder
+        if ctx.acts is None:
+            raise RuntimeError("vlp_b200: the fused BertLayer stack frees its activations in backward; a second backward "
+                               "(retain_graph=True) is not supported")
         x, acts = ctx.x, ctx.acts
         B, Lq, H = x.shape
         M = B * Lq
@@ -237,8 +235,8 @@ class EncoderStackFn(torch.autograd.Function):
             L.call("vlpk_f32_to_bf16", arena.data_ptr(), garena.data_ptr(), arena.numel(), L.stream())
         else:
             garena = arena
-        if _encoder_grad_hook is not None:
-            _encoder_grad_hook(garena)   # e.g. asynchronous NCCL all-reduce of this group's gradients (dp.GradientAllReducer)
+        if grad_hook is not None:
+            grad_hook(garena)            # e.g. asynchronous NCCL all-reduce of this group's gradients (dp.GradientAllReducer)
         grads = []
         for i in range(n_layers):
             for v, dt in zip(_grad_views(garena[i], H, I), ctx.param_dtypes[i * PARAMS_PER_LAYER:(i + 1) * PARAMS_PER_LAYER]):

@@ -71,6 +71,9 @@ class BertAdam(Optimizer):
                         max_grad_norm=max_grad_norm)
         super(BertAdam, self).__init__(params, defaults)
         self._keep = None     # device tables of the last step (kept alive until the next one)
+        self._plan = None     # cached per-group descriptor tables (see step())
+        self._plan_sig = None
+        self._pinned = {}     # (device, n tensors) -> rotating pinned host tables
 
     @staticmethod
     def _scheduled_lr(group, step):
@@ -110,6 +113,7 @@ class BertAdam(Optimizer):
         saved_groups = state_dict['param_groups']
         saved_state = state_dict['state']
         super(BertAdam, self).load_state_dict(state_dict)
+        self._plan = None
         ids = [i for g in saved_groups for i in g['params']]
         params = [p for g in self.param_groups for p in g['params']]
         for i, p in zip(ids, params):
@@ -142,12 +146,53 @@ class BertAdam(Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        # One launch pair per distinct (device, scheduled lr, b1, b2, e, max_grad_norm); in practice a single one:
-        # the two weight-decay groups of run_img2txt_dist.py:394-401 differ only in the per-tensor weight_decay field.
+        # Host side of a step = O(#tensors) pointer gathering only: everything that does not change between steps (parameter / state
+        # pointers, sizes, weight decay, dtype tags, chunk prefix, validation) is cached in a plan, rebuilt when the set of parameters
+        # that carry a gradient changes or state is (re)loaded.  One launch pair per distinct (device, scheduled lr, b1, b2, e,
+        # max_grad_norm); in practice a single one: the two weight-decay groups of run_img2txt_dist.py:394-401 differ only in the
+        # per-tensor weight_decay field.
+        sig = tuple((id(p), p.grad is None) for group in self.param_groups for p in group['params'])
+        if self._plan is not None and self._plan_sig == sig:
+            # state tensors replaced behind the plan's back (a hand-rolled state load, dtype casts): re-validate
+            for _, _, states, tab in self._plan:
+                if [st['next_m'].data_ptr() for st in states] != tab["m"].tolist() or [st['next_v'].data_ptr() for st in states] != tab["v"].tolist():
+                    self._plan = None
+                    break
+        if self._plan is None or self._plan_sig != sig:
+            self._build_plan()
+            self._plan_sig = sig
         buckets = {}
+        for group, ps, states, tab in self._plan:
+            if not ps:
+                continue
+            grads = []
+            for i, p in enumerate(ps):
+                g = p.grad
+                if g.dtype not in _DT or g.is_sparse:
+                    raise RuntimeError(f"vlp_b200 BertAdam: gradients must be dense bf16 or fp32, got {g.dtype}")
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                grads.append(g)
+            tab["grad"] = [g.data_ptr() for g in grads]
+            tab["grad_dtype"] = [_DT[g.dtype] for g in grads]
+            key = (ps[0].device, self._scheduled_lr(group, states[0]['step']), group['b1'], group['b2'], group['e'], group['max_grad_norm'])
+            buckets.setdefault(key, []).append((tab, grads, states))
+        keep = []
+        for (device, lr_s, b1, b2, e, max_norm), parts in buckets.items():
+            tab = parts[0][0] if len(parts) == 1 else np.concatenate([t for t, _, _ in parts])
+            keep.append(self._launch(device, tab, lr_s, b1, b2, e, max_norm) + ([g for _, gs, _ in parts for g in gs],))
+            for _, _, states in parts:
+                for state in states:
+                    state['step'] += 1
+        self._keep = keep
+        return loss
+
+    def _build_plan(self):
+        plan = []
         for group in self.param_groups:
+            ps, states = [], []
             for p in group['params']:
-                if p.grad is None:
+                if p.grad is None or p.numel() == 0:
                     continue
                 if p.grad.is_sparse:
                     raise RuntimeError('Adam does not support sparse gradients, please consider SparseAdam instead')
@@ -156,40 +201,43 @@ class BertAdam(Optimizer):
                 ops._require_cuda(p, "BertAdam parameters")
                 if not p.is_contiguous():
                     raise RuntimeError("vlp_b200 BertAdam: parameters must be contiguous")
-                if p.numel() == 0:
-                    continue
                 state = self._init_state(p)
-                key = (p.device, self._scheduled_lr(group, state['step']), group['b1'], group['b2'], group['e'], group['max_grad_norm'])
-                buckets.setdefault(key, []).append((p, state, float(group['weight_decay'])))
-        keep = []
-        for (device, lr_s, b1, b2, e, max_norm), items in buckets.items():
-            keep.append(self._launch(device, items, lr_s, b1, b2, e, max_norm))
-            for _, state, _ in items:
-                state['step'] += 1
-        self._keep = keep
-        return loss
+                for key in ('next_m', 'next_v', 'master'):
+                    t = state.get(key)
+                    if t is not None and not (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel() and t.device == p.device):
+                        raise RuntimeError(f"vlp_b200 BertAdam: state['{key}'] must be a contiguous fp32 tensor of the parameter's size on its "
+                                           f"device (got {t.dtype}, {tuple(t.shape)}, {t.device}); state loaded without BertAdam.load_state_dict?")
+                ps.append(p)
+                states.append(state)
+            tab = np.zeros(len(ps), dtype=_TENSOR_DTYPE)
+            wd = float(group['weight_decay'])
+            for i, (p, state) in enumerate(zip(ps, states)):
+                master = state.get('master')
+                tab[i] = (p.data_ptr(), 0, 0 if master is None else master.data_ptr(), state['next_m'].data_ptr(), state['next_v'].data_ptr(),
+                          p.numel(), wd, _DT[p.dtype], 0, 0)
+            plan.append((group, ps, states, tab))
+        self._plan = plan
 
-    @staticmethod
-    def _launch(device, items, lr_s, b1, b2, e, max_norm):
-        n = len(items)
+    def _launch(self, device, tab, lr_s, b1, b2, e, max_norm):
+        n = len(tab)
         chunk = L.lib().vlpk_bertadam_chunk()
-        tab = np.zeros(n, dtype=_TENSOR_DTYPE)
-        grads = []
-        for i, (p, state, wd) in enumerate(items):
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            grads.append(g)
-            master = state.get('master')
-            for key, t in (('next_m', state['next_m']), ('next_v', state['next_v']), ('master', master)):
-                if t is not None and not (t.dtype == torch.float32 and t.is_contiguous() and t.numel() == p.numel() and t.device == p.device):
-                    raise RuntimeError(f"vlp_b200 BertAdam: state['{key}'] must be a contiguous fp32 tensor of the parameter's size on its "
-                                       f"device (got {t.dtype}, {tuple(t.shape)}, {t.device}); state loaded without BertAdam.load_state_dict?")
-            tab[i] = (p.data_ptr(), g.data_ptr(), 0 if master is None else master.data_ptr(), state['next_m'].data_ptr(),
-                      state['next_v'].data_ptr(), p.numel(), wd, _DT[p.dtype], _DT[g.dtype], 0)
-        prefix = np.zeros(n + 1, dtype=np.int32)
+        # The descriptor table travels through PINNED host memory: an asynchronous copy from pageable memory synchronises the host
+        # with the stream, i.e. with the whole backward that is still in flight — a pipeline bubble of ~1 ms per step on a B200.
+        # Three rotating slots: a slot is rewritten two steps after its copy was enqueued (the copy has long completed by then).
+        slot = self._pinned.setdefault((device, n), {"i": 0, "bufs": [None, None, None]})
+        k = slot["i"] = (slot["i"] + 1) % 3
+        if slot["bufs"][k] is None:
+            pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)     # (CPU dry-run tests marshal without a GPU)
+            slot["bufs"][k] = (pin(torch.empty(n * _TENSOR_DTYPE.itemsize, dtype=torch.uint8)), pin(torch.empty(n + 1, dtype=torch.int32)))
+        tab_pin, prefix_pin = slot["bufs"][k]
+        tab_np = tab_pin.numpy().view(_TENSOR_DTYPE)
+        tab_np[:] = tab
+        prefix = prefix_pin.numpy()
+        prefix[0] = 0
         np.cumsum((tab["n"] + chunk - 1) // chunk, out=prefix[1:])
-        tab_dev = torch.from_numpy(tab.view(np.uint8)).to(device, non_blocking=True)
-        prefix_dev = torch.from_numpy(prefix).to(device, non_blocking=True)
+        tab_dev = tab_pin.to(device, non_blocking=True)
+        prefix_dev = prefix_pin.to(device, non_blocking=True)
         sqnorm = torch.empty(n, dtype=torch.float32, device=device)
-        L.call("vlpk_bertadam_step", tab.ctypes.data, tab_dev.data_ptr(), prefix.ctypes.data, prefix_dev.data_ptr(), n, sqnorm.data_ptr(),
+        L.call("vlpk_bertadam_step", tab_np.ctypes.data, tab_dev.data_ptr(), prefix.ctypes.data, prefix_dev.data_ptr(), n, sqnorm.data_ptr(),
                float(lr_s), float(b1), float(b2), float(e), float(max_norm), L.stream())
-        return tab_dev, prefix_dev, sqnorm, grads
+        return tab_dev, prefix_dev, sqnorm

@@ -245,6 +245,9 @@ class BertEncoder(nn.Module):
         # (data parallelism: a group's gradients are complete — and their all-reduce can start — while lower layers still run
         # backward; a small first group shortens the all-reduce that is exposed at the end of backward)
         self.layers_per_call = None
+        # data parallelism (vlp_b200/dp.py): callable(flat gradient arena of one layer group), invoked by the group's backward.  Owned by
+        # THIS module, so a second model / an eval copy in the same process is never touched.
+        self._vlpk_grad_hook = None
 
     def forward(self, hidden_states, attention_mask, prev_embedding=None, prev_encoded_layers=None, output_all_encoded_layers=True):
         assert (prev_embedding is None) == (prev_encoded_layers is None), \
@@ -280,7 +283,7 @@ class BertEncoder(nn.Module):
             params = []
             for l in group:
                 params.extend(l.flat_params())
-            g_outs = ops.EncoderStackFn.apply(cur, bits, self.layer[0]._cfg(len(group)), *params)
+            g_outs = ops.EncoderStackFn.apply(cur, bits, self.layer[0]._cfg(len(group)) + (self._vlpk_grad_hook,), *params)
             outs.extend(g_outs)
             cur = g_outs[-1]
         outs = [o if o.dtype == dt else o.to(dt) for o in outs]
