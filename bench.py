@@ -294,6 +294,31 @@ def main():
         dist.all_gather(allc, chk)
         assert all(torch.equal(allc[0], c) for c in allc), f"gradients differ across ranks after all-reduce: {allc}"
 
+    if reducer is not None:
+        # numerical check of the reducer (dropout off so that two runs see the same function): local gradients averaged with plain
+        # all_reduce calls vs what the overlapped / sparse-row path leaves in .grad
+        model.eval()
+        probe = {"word": model.bert.embeddings.word_embeddings.weight, "pos": model.bert.embeddings.position_embeddings.weight,
+                 "l0.q": model.bert.encoder.layer[0].attention.self.query.weight, "l11.w2": model.bert.encoder.layer[11].output.dense.weight,
+                 "vis0": model.vis_embed[0].weight, "cls.bias": model.cls.predictions.bias, "type": model.bert.embeddings.token_type_embeddings.weight}
+        reducer.enabled = False
+        one_step(dev_batch)
+        want = {}
+        probe = {k: p for k, p in probe.items() if p.grad is not None}      # (the VQA objective leaves the MLM head without gradient)
+        assert len(probe) >= 5
+        for k, p in probe.items():
+            g = p.grad.detach().float().clone()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            want[k] = g / world
+        reducer.enabled = True
+        one_step(dev_batch)
+        for k, p in probe.items():
+            err = float((p.grad.float() - want[k]).norm() / (want[k].norm() + 1e-30))
+            assert err < 2e-2, f"reducer check failed for {k}: rel err {err}"
+        model.train()
+        for _ in range(2):
+            one_step(dev_batch)
+
     launches0 = L.lib().vlpk_launch_count()
     with ClockSampler(local_rank) as clocks:
         ms_total, per_step = timed_loop(args.steps)

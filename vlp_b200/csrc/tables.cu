@@ -127,30 +127,109 @@ __global__ void __launch_bounds__(256) type_grad_kernel(TableGradArgs a) {
   }
 }
 
+// Explicit row lists (data parallelism, vlp_b200/dp.py): the looked-up rows of ALL ranks (all-gathered: 23 rows per sample instead of
+// all-reducing the dense [V,H] table gradient) are added, scaled by 1/world, INTO an existing bf16 word-table gradient — the tied
+// decoder weight's gradient, whose own all-reduce was issued as soon as the head's backward produced it — and into the fp32 position
+// gradient.  Duplicate ids (every [CLS] / [SEP]) are summed in fp32 first; one warp per id (elected through `owner`) does the bf16 update.
+template <int PHASE>
+__global__ void __launch_bounds__(256) table_rows_kernel(TableRowsArgs a) {
+  const long long e = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (e >= a.n) return;
+  const int lane = threadIdx.x & 31;
+  const long long id = a.ids[e];
+  const bool id_ok = (id >= 0 && id < a.V);
+  const long long p = (a.pos != nullptr) ? a.pos[e] : -1;
+  const bool p_ok = (a.d_pos != nullptr && p >= 0 && p < a.P);
+  bool won = false;
+  if (PHASE == 0) {
+    if (id_ok && lane == 0) a.owner[id] = 0;
+  } else if (PHASE == 2) {
+    int w = 0;
+    if (id_ok && lane == 0) w = (atomicExch(a.owner + id, 1) == 0) ? 1 : 0;
+    won = __shfl_sync(0xffffffffu, w, 0) != 0;
+    if (!won) return;
+  }
+  for (int c = lane * 8; c < a.H; c += 256) {
+    if (PHASE == 0) {
+      if (id_ok) {
+        float* d = a.scratch + id * a.H + c;
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(d + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    } else if (PHASE == 1) {
+      float v[8];
+      ld8(a.rows + e * a.H + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= a.scale;
+      if (id_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(a.scratch + id * a.H + c + j, v[j]);
+      }
+      if (p_ok) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(a.d_pos + p * a.H + c + j, v[j]);
+      }
+    } else {
+      float cur[8];
+      ld8(a.d_word + id * a.H + c, cur);
+      const float* sp = a.scratch + id * a.H + c;
+      const float4 x = *reinterpret_cast<const float4*>(sp), y = *reinterpret_cast<const float4*>(sp + 4);
+      *reinterpret_cast<uint4*>(a.d_word + id * a.H + c) =
+          make_uint4(pack_bf16x2(cur[0] + x.x, cur[1] + x.y), pack_bf16x2(cur[2] + x.z, cur[3] + x.w), pack_bf16x2(cur[4] + y.x, cur[5] + y.y),
+                     pack_bf16x2(cur[6] + y.z, cur[7] + y.w));
+    }
+  }
+}
+
 }  // namespace
+
+int launch_table_rows_add(const TableRowsArgs& a, cudaStream_t s) {
+  VLPK_CHECK_ARG(a.n > 0 && a.H > 0 && a.H % 8 == 0 && a.V > 0, "table_rows_add: n=%lld H=%d V=%d", a.n, a.H, a.V);
+  VLPK_CHECK_ARG(a.ids && a.rows && a.d_word && a.scratch && a.owner, "table_rows_add: null pointer");
+  VLPK_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.rows) | reinterpret_cast<uintptr_t>(a.d_word) | reinterpret_cast<uintptr_t>(a.scratch)) & 15u) == 0,
+                 "table_rows_add: rows / d_word / scratch must be 16-byte aligned");
+  const unsigned grid = static_cast<unsigned>((a.n + 7) / 8);
+  {
+    LaunchScope scope(CAT_EMBED, 0.0, s);
+    table_rows_kernel<0><<<grid, 256, 0, s>>>(a);
+    VLPK_CUDA(cudaGetLastError());
+  }
+  {
+    LaunchScope scope(CAT_EMBED, 0.0, s);
+    table_rows_kernel<1><<<grid, 256, 0, s>>>(a);
+    VLPK_CUDA(cudaGetLastError());
+  }
+  LaunchScope scope(CAT_EMBED, 0.0, s);
+  table_rows_kernel<2><<<grid, 256, 0, s>>>(a);
+  VLPK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launch_embed_tables_bwd(const TableGradArgs& a, cudaStream_t s) {
   VLPK_CHECK_ARG(a.B > 0 && a.L > 0 && a.H > 0 && a.H % 8 == 0, "embed_tables_bwd: B=%d L=%d H=%d (H must be a multiple of 8)", a.B, a.L, a.H);
   VLPK_CHECK_ARG(a.V > 0 && a.P > 0 && a.T > 0 && a.T <= TT_MAX, "embed_tables_bwd: V=%d P=%d T=%d (at most %d token types)", a.V, a.P, a.T, TT_MAX);
   VLPK_CHECK_ARG(!a.vis_input || (a.R > 0 && a.R < a.L), "embed_tables_bwd: R=%d regions do not fit L=%d", a.R, a.L);
-  VLPK_CHECK_ARG(a.ids && a.dz && a.d_word && a.scratch && a.d_pos && a.d_type, "embed_tables_bwd: null pointer");
+  const bool type_only = (a.d_word == nullptr && a.scratch == nullptr && a.d_pos == nullptr);   // word / position rows handled elsewhere
+  VLPK_CHECK_ARG(a.ids && a.dz && a.d_type && (type_only || (a.d_word && a.scratch && a.d_pos)), "embed_tables_bwd: null pointer");
   VLPK_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.dz) | reinterpret_cast<uintptr_t>(a.d_word) | reinterpret_cast<uintptr_t>(a.scratch)) & 15u) == 0,
                  "embed_tables_bwd: dz / d_word / scratch must be 16-byte aligned");
   const long long M = static_cast<long long>(a.B) * a.L;
   const long long n_entries = static_cast<long long>(a.B) * (a.vis_input ? a.L - a.R : a.L);
-  VLPK_CUDA(cudaMemsetAsync(a.d_word, 0, static_cast<size_t>(a.V) * a.H * 2, s));
   const unsigned grid = static_cast<unsigned>((n_entries + 7) / 8);
-  {
+  if (!type_only) {
+    VLPK_CUDA(cudaMemsetAsync(a.d_word, 0, static_cast<size_t>(a.V) * a.H * 2, s));
+  }
+  if (!type_only) {
     LaunchScope scope(CAT_EMBED, 0.0, s);
     word_pos_kernel<0><<<grid, 256, 0, s>>>(a, n_entries);
     VLPK_CUDA(cudaGetLastError());
   }
-  {
+  if (!type_only) {
     LaunchScope scope(CAT_EMBED, 0.0, s);
     word_pos_kernel<1><<<grid, 256, 0, s>>>(a, n_entries);
     VLPK_CUDA(cudaGetLastError());
   }
-  {
+  if (!type_only) {
     LaunchScope scope(CAT_EMBED, 2.0 * a.V * a.H, s);
     word_pos_kernel<2><<<grid, 256, 0, s>>>(a, n_entries);
     VLPK_CUDA(cudaGetLastError());
