@@ -211,6 +211,14 @@ int vlpk_mha_bwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
  * inference only (no dropout, nothing saved for backward).  x: [B*Lq,H] new rows; x_kv = cat(history, x): [B*Lkv,H]. */
 int vlpk_mha_incr_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* mask_bits,
                       int mask_rows, VlpkLayerActs* a, uint64_t layer_id, void* stream);
+/* BertLayer.forward for incremental decode with a persistent K/V cache (the reference re-projects K and V of the whole
+ * prefix at every step, modeling.py:273-277).  kv_cache [B, cache_rows, 2H] bf16 holds key | value projections of the rows this layer has
+ * already seen; `pos` of them are valid.  The Lq new rows x [B*Lq, H] are projected, their K | V appended at rows [pos, pos + Lq), attention
+ * runs over rows [0, pos + Lq) (s->Lkv must equal pos + s->Lq), then output projection, LayerNorm and FFN as vlpk_layer_fwd (no dropout).
+ * a->qkv receives Q [B*Lq, H]; a->kv [B*Lq, 2H] is scratch for the new rows' K | V.  A later call may overwrite rows (decode keeps only
+ * the rows of real tokens: the [MASK] row written at pos + Lq - 1 is overwritten by the next step). */
+int vlpk_layer_cached_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, void* kv_cache, int cache_rows, int pos,
+                          const uint32_t* mask_bits, int mask_rows, VlpkLayerActs* a, uint64_t layer_id, void* stream);
 /* Host-only: bytes the caller must provide for a shape.  out3 = { all VlpkLayerActs buffers of ONE layer (without the optional
  * drop_attn keep-bytes: B*heads*Lq*16),
  * all VlpkBwdScratch buffers (shared by the layers), the fp32 VlpkLayerGrads accumulators of ONE layer }. */

@@ -183,13 +183,13 @@ def pretraining_loss(sd, dims, batch, tasks="img2txt", drop_worst_ratio=0.0, p_h
     return losses
 
 
-def greedy_decode(sd, dims, vis_feats, vis_pe, input_ids, token_type_ids, position_ids, attention_mask, mask_word_id):
+def greedy_decode(sd, dims, vis_feats, vis_pe, input_ids, token_type_ids, position_ids, attention_mask, mask_word_id, return_gaps=False):
     """BertForSeq2SeqDecoder.forward greedy branch, modeling.py:1189-1253, with BertModelIncr (:856-875):
     step 0 encodes [CLS] regions [SEP] [MASK]; later steps feed (new token, [MASK]) with cached layer inputs."""
     vis, vpe = region_projections(sd, vis_feats, vis_pe)
     B, in_len = input_ids.shape
     out_len = token_type_ids.shape[1]
-    out_ids, out_scores = [], []
+    out_ids, out_scores, out_gaps = [], [], []
     prev_emb, prev_layers = None, None
     curr = input_ids
     mask_ids = input_ids[:, :1] * 0 + mask_word_id
@@ -208,6 +208,8 @@ def greedy_decode(sd, dims, vis_feats, vis_pe, input_ids, token_type_ids, positi
         mx, ids = torch.max(scores, dim=-1)
         out_ids.append(ids)
         out_scores.append(mx)
+        top2 = torch.topk(scores, 2, dim=-1).values
+        out_gaps.append(top2[..., 0] - top2[..., 1])          # margin of the argmax: a reduced-precision run may flip it only when tiny
         if prev_emb is None:
             prev_emb = emb[:, :-1, :]
             prev_layers = [x[:, :-1, :] for x in layers]
@@ -216,4 +218,6 @@ def greedy_decode(sd, dims, vis_feats, vis_pe, input_ids, token_type_ids, positi
             prev_layers = [torch.cat((a, b[:, :-1, :]), dim=1) for a, b in zip(prev_layers, layers)]
         curr = ids
         nxt += 1
+    if return_gaps:
+        return torch.cat(out_ids, dim=1), torch.cat(out_scores, dim=1), torch.cat(out_gaps, dim=1)
     return torch.cat(out_ids, dim=1), torch.cat(out_scores, dim=1)

@@ -1,9 +1,12 @@
 """Beam search for BertForSeq2SeqDecoder (semantics of the reference's modeling.py:1256-1494).
 
-Same algorithm and return format (a `traces` dict of padded tensors: pred_seq, scores, wids, ptrs), with the
-beam bookkeeping kept on the device and the back-pointer computed by integer floor division — the reference's
-`torch.div(k_ids, K)` (:1317) yields floats on torch >= 1.6 and breaks `gather`.
-Every step runs the incremental fused layers (q rows = new token + [MASK], kv rows = cached prefix + q).
+Same algorithm and return format (a `traces` dict of padded tensors: pred_seq, scores, wids, ptrs), with ALL beam
+bookkeeping on the device — top-k, back pointers (integer floor division: the reference's `torch.div(k_ids, K)`, :1317, yields
+floats on torch >= 1.6 and breaks `gather`), the per-layer K/V caches reordered by the back pointers, and the final
+best-hypothesis selection + back-tracking (:1431-1472) as vectorised tensor ops: no host synchronisation inside or after the loop
+(the optional duplicate-n-gram filter is the one host-side piece, as in the reference).
+Every step runs the fused layers on the two new rows (token, [MASK]) against the K/V caches (`dec.use_kv_cache`), or — reference
+data flow — against the re-encoded prefix.
 """
 import math
 
@@ -43,6 +46,7 @@ def beam_search(dec, vis_feats, vis_pe, input_ids, token_type_ids, position_ids,
     out_len = token_type_ids.shape[1]
     dev = input_ids.device
     prev_emb, prev_layers = None, None
+    caches = dec.new_kv_caches(B, dev) if getattr(dec, "use_kv_cache", False) else None
     curr_ids = input_ids
     mask_ids = input_ids[:, :1] * 0 + dec.mask_word_id
     total_scores, beam_eos, step_ids, step_ptrs = [], [], [], []
@@ -52,9 +56,15 @@ def beam_search(dec, vis_feats, vis_pe, input_ids, token_type_ids, position_ids,
         cl = curr_ids.shape[1]
         st = next_pos - cl
         x_ids = torch.cat((curr_ids, mask_ids), dim=1)
-        new_emb, new_layers, _ = dec.bert(vis_feats, vis_pe, x_ids, token_type_ids[:, st:next_pos + 1], position_ids[:, st:next_pos + 1],
-                                          attention_mask[:, st:next_pos + 1, :next_pos + 1], prev_embedding=prev_emb,
-                                          prev_encoded_layers=prev_layers, output_all_encoded_layers=True, len_vis_input=dec.len_vis_input)
+        if caches is not None:
+            new_emb, last, _ = dec.bert(vis_feats, vis_pe, x_ids, token_type_ids[:, st:next_pos + 1], position_ids[:, st:next_pos + 1],
+                                        attention_mask[:, st:next_pos + 1, :next_pos + 1], output_all_encoded_layers=False,
+                                        len_vis_input=dec.len_vis_input, kv_caches=caches, cache_pos=st)
+            new_layers = [last]
+        else:
+            new_emb, new_layers, _ = dec.bert(vis_feats, vis_pe, x_ids, token_type_ids[:, st:next_pos + 1], position_ids[:, st:next_pos + 1],
+                                              attention_mask[:, st:next_pos + 1, :next_pos + 1], prev_embedding=prev_emb,
+                                              prev_encoded_layers=prev_layers, output_all_encoded_layers=True, len_vis_input=dec.len_vis_input)
         scores, _ = dec.cls(new_layers[-1][:, -1:, :], None, task_idx=task_idx)
         logp = F.log_softmax(scores.float(), dim=-1)                      # [B or B*K, 1, V]
         if forbid is not None:
@@ -62,7 +72,7 @@ def beam_search(dec, vis_feats, vis_pe, input_ids, token_type_ids, position_ids,
         if dec.min_len and (next_pos - in_len + 1 <= dec.min_len):
             logp[:, :, dec.eos_id] = -10000.0
         kk_scores, kk_ids = torch.topk(logp, k=K)                          # [*, 1, K]
-        first = prev_emb is None
+        first = (next_pos == in_len)
         if first:
             k_ids = kk_ids.reshape(B, K)
             back = torch.zeros(B, K, dtype=torch.long, device=dev)
@@ -77,11 +87,16 @@ def beam_search(dec, vis_feats, vis_pe, input_ids, token_type_ids, position_ids,
         beam_eos.append((k_ids == dec.eos_id).float())
         total_scores.append(k_scores)
         if first:
-            prev_emb = _expand_beams(new_emb[:, :-1, :], K)
-            prev_layers = [_expand_beams(x[:, :-1, :], K) for x in new_layers]
+            if caches is not None:
+                caches = [_expand_beams(c, K).contiguous() for c in caches]
+            else:
+                prev_emb = _expand_beams(new_emb[:, :-1, :], K)
+                prev_layers = [_expand_beams(x[:, :-1, :], K) for x in new_layers]
             token_type_ids, position_ids = _expand_beams(token_type_ids, K), _expand_beams(position_ids, K)
             attention_mask, mask_ids = _expand_beams(attention_mask, K), _expand_beams(mask_ids, K)
-            vis_feats_k, vis_pe_k = vis_feats, vis_pe                      # regions only enter at step 0
+        elif caches is not None:
+            parent = (back + torch.arange(B, device=dev).unsqueeze(1) * K).reshape(-1)      # beam i continues hypothesis parent[i]
+            caches = [c.index_select(0, parent) for c in caches]
         else:
             prev_emb = _reorder(torch.cat((prev_emb, new_emb[:, :-1, :]), dim=1), back, B, K)
             prev_layers = [_reorder(torch.cat((a, b[:, :-1, :]), dim=1), back, B, K) for a, b in zip(prev_layers, new_layers)]
@@ -102,44 +117,36 @@ def beam_search(dec, vis_feats, vis_pe, input_ids, token_type_ids, position_ids,
                             forbid[i, 0, c] = 1.0
         next_pos += 1
 
-    # host-side back-tracking, identical selection rule to the reference (:1431-1472)
-    ts = [x.tolist() for x in total_scores]
-    si = [x.tolist() for x in step_ids]
-    sp = [x.tolist() for x in step_ptrs]
-    traces = {"pred_seq": [], "scores": [], "wids": [], "ptrs": []}
-    for b in range(B):
-        scores = [x[b] for x in ts]
-        wids_list = [x[b] for x in si]
-        ptrs = [x[b] for x in sp]
-        traces["scores"].append(scores)
-        traces["wids"].append(wids_list)
-        traces["ptrs"].append(ptrs)
-        last = len(scores) - 1
-        for i, w in enumerate(wids_list):
-            if all(x == dec.eos_id for x in w):
-                last = i
-                break
-        best, frame, pos = -math.inf, -1, -1
-        for fid in range(last + 1):
-            for i, w in enumerate(wids_list[fid]):
-                if w == dec.eos_id or fid == last:
-                    s = scores[fid][i] + dec.length_penalty * (fid + 1)
-                    if s > best:
-                        best, frame, pos = s, fid, i
-        if frame == -1:
-            traces["pred_seq"].append([0])
-        else:
-            seq = [wids_list[frame][pos]]
-            for fid in range(frame, 0, -1):
-                pos = ptrs[fid][pos]
-                seq.append(wids_list[fid - 1][pos])
-            traces["pred_seq"].append(seq[::-1])
-    out = {}
-    for k, lst in traces.items():
-        dt = torch.float if k == "scores" else torch.long
-        tens = [torch.tensor(x, dtype=dt) for x in lst]
-        padded = tens[0].new_zeros((len(tens), out_len) + tuple(tens[0].shape[1:]))
-        for i, t in enumerate(tens):
-            padded[i, :t.shape[0]] = t
-        out[k] = padded.to(dev)
+    out = {"pred_seq": backtrack(torch.stack(total_scores), torch.stack(step_ids), torch.stack(step_ptrs), dec.eos_id, dec.length_penalty, out_len)}
+    T = len(total_scores)
+    for k, t in (("scores", torch.stack(total_scores)), ("wids", torch.stack(step_ids)), ("ptrs", torch.stack(step_ptrs))):
+        padded = t.new_zeros((B, out_len, K))
+        padded[:, :T] = t.permute(1, 0, 2)
+        out[k] = padded
     return out
+
+
+def backtrack(sc, wi, pt, eos_id, length_penalty, out_len):
+    """Best-hypothesis selection + back-tracking, same rule as the reference (:1431-1472), vectorised (runs wherever the traces live):
+      last[b]   = first frame whose K words are all [EOS] (else the final frame)
+      candidate = (word is [EOS], or frame == last[b]) within frames <= last[b]; score + length_penalty * (frame + 1); FIRST maximum wins
+    sc [T,B,K] float scores, wi [T,B,K] word ids, pt [T,B,K] back pointers -> pred_seq [B, out_len] (zero padded)."""
+    T, B, K = sc.shape
+    dev = sc.device
+    frames = torch.arange(T, device=dev).view(T, 1)
+    all_eos = (wi == eos_id).all(-1)                                      # [T,B]
+    last = torch.where(all_eos.any(0), all_eos.float().argmax(0), torch.full((B,), T - 1, device=dev))      # [B]
+    cand = (frames <= last.unsqueeze(0)).unsqueeze(-1) & ((wi == eos_id) | (frames == last.unsqueeze(0)).unsqueeze(-1))
+    val = torch.where(cand, sc + length_penalty * (frames + 1).unsqueeze(-1).to(sc.dtype), torch.full_like(sc, -math.inf))
+    flat = val.permute(1, 0, 2).reshape(B, T * K)                          # (frame, beam) order = the reference's loop order
+    best = flat.argmax(-1)                                                # first maximal value
+    frame, pos = torch.div(best, K, rounding_mode="floor"), best % K
+    found = torch.isfinite(flat.gather(1, best.unsqueeze(1)).squeeze(1))
+    pred = torch.zeros(B, out_len, dtype=torch.long, device=dev)
+    bidx = torch.arange(B, device=dev)
+    for fid in range(T - 1, -1, -1):                                      # walk the back pointers from `frame` down to 0
+        active = found & (fid <= frame)
+        tok = wi[fid, bidx, pos]
+        pred[:, fid] = torch.where(active, tok, pred[:, fid])
+        pos = torch.where(active & (fid > 0), pt[fid, bidx, pos], pos)
+    return pred

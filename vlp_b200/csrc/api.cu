@@ -149,10 +149,17 @@ int wgrad_join(cudaStream_t main) {
   return 0;
 }
 
+struct KvCache {       // incremental decode with a persistent K/V cache (vlpk_layer_cached_fwd)
+  void* base = nullptr;  // [B, rows, 2H] bf16: key | value projections of the rows this layer has seen
+  int rows = 0;          // allocated rows per sequence
+  int pos = 0;           // rows already valid; the call appends the Lq new rows at [pos, pos + Lq)
+};
+
 int mha_fwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, const void* x_kv, const uint32_t* bits, int mask_rows,
-                 VlpkLayerActs* a, float p_attn, float p_hidden, const VlpkDropout* drop, uint64_t layer_id, cudaStream_t st) {
+                 VlpkLayerActs* a, float p_attn, float p_hidden, const VlpkDropout* drop, uint64_t layer_id, cudaStream_t st,
+                 const KvCache* cache = nullptr) {
   const int H = s->H, Mq = s->B * s->Lq, Mkv = s->B * s->Lkv;
-  const bool incr = (x_kv != nullptr && x_kv != x);
+  const bool incr = (cache == nullptr && x_kv != nullptr && x_kv != x);
   const DropoutCfg none = make_dropout(0.f, 0, 0);
   AttnDesc ad;
   ad.B = s->B; ad.heads = s->heads; ad.Lq = s->Lq; ad.Lkv = s->Lkv;
@@ -160,7 +167,30 @@ int mha_fwd_impl(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, c
   ad.o = a->ctx; ad.ld_o = H; ad.lse = a->lse;
   ad.drop = mk_drop(drop, p_attn, site_of(layer_id, SITE_ATTN));
   ad.keep_out = (ad.drop.p > 0.f) ? a->drop_attn : nullptr;   // forward stores its keep-decisions for backward
-  if (!incr) {
+  if (cache != nullptr) {
+    // Q and K|V of the NEW rows only; K|V are appended to the cache (rows [pos, pos + Lq) of every sequence), attention reads the cache
+    VLPK_CHECK_ARG(a->kv != nullptr && cache->base != nullptr && cache->pos >= 0 && cache->pos + s->Lq == s->Lkv && s->Lkv <= cache->rows,
+                   "mha_cached_fwd: pos=%d + Lq=%d must equal Lkv=%d <= cache rows %d", cache->pos, s->Lq, s->Lkv, cache->rows);
+    VLPK_TRY(fwd_linear(Mq, H, H, x, H, w->wq, H, w->bq, a->qkv, H, EPI_STORE, nullptr, 0, none, st));
+    GemmDesc g;
+    g.M = Mq; g.N = 2 * H; g.K = H;
+    g.A = x; g.lda = H;
+    g.nseg = 2; g.b_seg_rows = H; g.ldb = H;
+    g.B[0] = w->wk; g.B[1] = w->wv;
+    g.bias[0] = static_cast<const bf16*>(w->bk); g.bias[1] = static_cast<const bf16*>(w->bv);
+    g.D0 = a->kv; g.ldd0 = 2 * H;
+    g.epi = EPI_STORE;
+    g.bn = (H % 256 == 0) ? 0 : 128;
+    VLPK_TRY(launch_gemm(g, st));
+    bf16* dst = static_cast<bf16*>(cache->base) + static_cast<size_t>(cache->pos) * 2 * H;
+    VLPK_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(cache->rows) * 2 * H * sizeof(bf16), a->kv, static_cast<size_t>(s->Lq) * 2 * H * sizeof(bf16),
+                                static_cast<size_t>(s->Lq) * 2 * H * sizeof(bf16), s->B, cudaMemcpyDeviceToDevice, st));
+    ad.q = a->qkv; ad.ld_q = H;
+    ad.k = cache->base;
+    ad.v = static_cast<const bf16*>(cache->base) + H;
+    ad.ld_kv = 2 * H;
+    ad.kv_batch_stride = static_cast<int64_t>(cache->rows) * 2 * H;
+  } else if (!incr) {
     VLPK_CHECK_ARG(s->Lq == s->Lkv, "mha_fwd: Lq != Lkv requires x_kv");
     GemmDesc g;  // packed QKV projection: three [H,H] weights read in place as N-segments
     g.M = Mq; g.N = 3 * H; g.K = H;
@@ -585,6 +615,16 @@ int vlpk_mha_incr_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void*
   VLPK_TRY(check_shape(s));
   VLPK_CHECK_ARG(w && x && x_kv && x_kv != x && mask_bits && a, "mha_incr_fwd: needs x, x_kv (= cat(history, x)), mask and acts");
   return mha_fwd_impl(s, w, x, x_kv, mask_bits, mask_rows, a, 0.f, 0.f, nullptr, layer_id, S(stream));
+}
+
+int vlpk_layer_cached_fwd(const VlpkShape* s, const VlpkLayerWeights* w, const void* x, void* kv_cache, int cache_rows, int pos,
+                          const uint32_t* mask_bits, int mask_rows, VlpkLayerActs* a, uint64_t layer_id, void* stream) {
+  VLPK_TRY(check_shape(s));
+  VLPK_CHECK_ARG(w && x && kv_cache && mask_bits && a, "layer_cached_fwd: null pointer");
+  KvCache c;
+  c.base = kv_cache; c.rows = cache_rows; c.pos = pos;
+  VLPK_TRY(mha_fwd_impl(s, w, x, nullptr, mask_bits, mask_rows, a, 0.f, 0.f, nullptr, layer_id, S(stream), &c));
+  return ffn_fwd_impl(s, w, a, 0.f, nullptr, layer_id, S(stream));
 }
 
 int vlpk_workspace_bytes(const VlpkShape* s, size_t* out3) {

@@ -607,9 +607,10 @@ __global__ void __launch_bounds__(ATT_BWD_THREADS, 2) attn_bwd_kernel(const __gr
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int make_seq_tmap(CUtensorMap* out, const void* base, int width, int L, int B, int64_t ld) {
+static int make_seq_tmap(CUtensorMap* out, const void* base, int width, int L, int B, int64_t ld, int64_t batch_stride = 0) {
   uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(L), static_cast<uint64_t>(B)};
-  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(L)};
+  uint64_t strides[2] = {static_cast<uint64_t>(ld) * 2,
+                         batch_stride > 0 ? static_cast<uint64_t>(batch_stride) * 2 : static_cast<uint64_t>(ld) * 2 * static_cast<uint64_t>(L)};
   uint32_t box[3] = {HD, TL, 1};
   return make_tmap(out, TM_BF16, 3, base, dims, strides, box);
 }
@@ -630,8 +631,8 @@ int launch_attn_fwd(const AttnDesc& d, cudaStream_t stream) {
   AttnTmaps tm;
   memset(&tm, 0, sizeof(tm));
   VLPK_TRY(make_seq_tmap(&tm.q, d.q, width, d.Lq, d.B, d.ld_q));
-  VLPK_TRY(make_seq_tmap(&tm.k, d.k, width, d.Lkv, d.B, d.ld_kv));
-  VLPK_TRY(make_seq_tmap(&tm.v, d.v, width, d.Lkv, d.B, d.ld_kv));
+  VLPK_TRY(make_seq_tmap(&tm.k, d.k, width, d.Lkv, d.B, d.ld_kv, d.kv_batch_stride));
+  VLPK_TRY(make_seq_tmap(&tm.v, d.v, width, d.Lkv, d.B, d.ld_kv, d.kv_batch_stride));
   VLPK_TRY(make_seq_tmap(&tm.o, d.o, width, d.Lq, d.B, d.ld_o));
   tm.dq = tm.dk = tm.dv = tm.o;
   AttnArgs a;

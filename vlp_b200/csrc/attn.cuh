@@ -12,6 +12,7 @@ struct AttnDesc {
   const void* k = nullptr;
   const void* v = nullptr;
   int64_t ld_q = 0, ld_kv = 0;
+  int64_t kv_batch_stride = 0;  // elements between consecutive sequences of K / V (0 = Lkv * ld_kv); a K/V cache has cache_rows * ld_kv
   void* o = nullptr;  // ctx [B, Lq, ld_o]   (bwd: forward output, read for delta)
   int64_t ld_o = 0;
   const uint32_t* mask_bits = nullptr;  // [B, mask_rows, 4] packed by vlpk_mask_pack

@@ -431,3 +431,20 @@ class DecoderCEFn(torch.autograd.Function):
         if ctx.dp_hook is not None:
             ctx.dp_hook.on_decoder_weight_grad(dwp)      # data parallelism: this (tied) gradient is complete FIRST — reduce it now
         return dh.to(hdt), dwp, dbias[:V].to(bdt), None, None
+
+
+def layer_cached_fwd(hidden, kv_cache, pos, mask_bits, heads, I, params):
+    """BertLayer.forward for decode with a persistent K/V cache (vlpk_layer_cached_fwd): `hidden` [B, Lq, H] are the new rows, `kv_cache`
+    [B, rows, 2H] bf16 holds this layer's key | value projections of the `pos` rows already seen; the new rows' K | V are appended at
+    [pos, pos + Lq).  Inference only."""
+    x = _bf16c(hidden)
+    B, Lq, H = x.shape
+    if not (kv_cache.dtype == BF16 and kv_cache.is_contiguous() and kv_cache.shape[0] == B and kv_cache.shape[2] == 2 * H):
+        raise RuntimeError("vlp_b200: kv_cache must be a contiguous bf16 [B, rows, 2H] tensor")
+    pk = [_bf16c(p) for p in params]
+    acts = _Acts(1, B, Lq, H, heads, I, x.device, Lkv=Lq)            # acts.kv: scratch for the new rows' K | V
+    shape = L.VlpkShape(B, Lq, pos + Lq, H, heads, I)
+    ws = _weight_structs(pk, 1)
+    L.call("vlpk_layer_cached_fwd", C.byref(shape), ws, x.data_ptr(), kv_cache.data_ptr(), kv_cache.shape[1], int(pos), mask_bits.data_ptr(),
+           mask_bits.shape[1], acts.structs, 0, L.stream())
+    return acts.y[0]

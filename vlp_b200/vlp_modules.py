@@ -224,9 +224,15 @@ class BertLayer(nn.Module):
     def _cfg(self, n_layers):
         return (n_layers, self._heads, self._inter, float(self.attention.self.dropout.p), float(self.output.dropout.p), self.training)
 
-    def forward(self, hidden_states, attention_mask, history_states=None):
+    def forward(self, hidden_states, attention_mask, history_states=None, kv_cache=None, cache_pos=0):
+        """Reference signature (modeling.py:367) plus an optional decode extension: `kv_cache` [B, rows, 2H] (this layer's key | value
+        projections of the `cache_pos` rows already decoded) replaces `history_states` — K and V of the prefix are not re-projected."""
         bits = _mask_bits(attention_mask)
-        if history_states is None:
+        if kv_cache is not None:
+            if torch.is_grad_enabled() and (hidden_states.requires_grad or any(p.requires_grad for p in self.flat_params())):
+                raise RuntimeError("vlp_b200: BertLayer with kv_cache is an inference-only path (decode); wrap in torch.no_grad()")
+            out = ops.layer_cached_fwd(hidden_states, kv_cache, cache_pos, bits, self._heads, self._inter, self.flat_params())
+        elif history_states is None:
             out = ops.EncoderStackFn.apply(hidden_states, bits, self._cfg(1), *self.flat_params())[0]
         else:
             if torch.is_grad_enabled() and (hidden_states.requires_grad or any(p.requires_grad for p in self.flat_params())):
@@ -250,9 +256,19 @@ class BertEncoder(nn.Module):
         # THIS module, so a second model / an eval copy in the same process is never touched.
         self._vlpk_grad_hook = None
 
-    def forward(self, hidden_states, attention_mask, prev_embedding=None, prev_encoded_layers=None, output_all_encoded_layers=True):
+    def forward(self, hidden_states, attention_mask, prev_embedding=None, prev_encoded_layers=None, output_all_encoded_layers=True,
+                kv_caches=None, cache_pos=0):
         assert (prev_embedding is None) == (prev_encoded_layers is None), \
             "history embedding and encoded layer must be simultanously given."
+        if kv_caches is not None:                            # decode with per-layer K/V caches
+            all_layers = []
+            for layer_module, cache in zip(self.layer, kv_caches):
+                hidden_states = layer_module(hidden_states, attention_mask, kv_cache=cache, cache_pos=cache_pos)
+                if output_all_encoded_layers:
+                    all_layers.append(hidden_states)
+            if not output_all_encoded_layers:
+                all_layers.append(hidden_states)
+            return all_layers
         if prev_embedding is not None:
             all_layers = []
             history_states = prev_embedding
@@ -464,12 +480,15 @@ class BertModelIncr(BertModel):
     """modeling.py:852-875."""
 
     def forward(self, vis_feats, vis_pe, input_ids, token_type_ids, position_ids, attention_mask, prev_embedding=None, prev_encoded_layers=None,
-                output_all_encoded_layers=True, len_vis_input=49):
+                output_all_encoded_layers=True, len_vis_input=49, kv_caches=None, cache_pos=0):
+        """Reference signature (modeling.py:856) plus `kv_caches` / `cache_pos`: decode against per-layer K/V caches instead of
+        re-encoding `prev_embedding` / `prev_encoded_layers` (regions enter at cache_pos == 0 only)."""
         ext = self.get_extended_attention_mask(input_ids, token_type_ids, attention_mask)
-        embedding_output = self.embeddings(vis_feats, vis_pe, input_ids, token_type_ids, position_ids, vis_input=(prev_encoded_layers is None),
+        first = (prev_encoded_layers is None) if kv_caches is None else (cache_pos == 0)
+        embedding_output = self.embeddings(vis_feats, vis_pe, input_ids, token_type_ids, position_ids, vis_input=first,
                                            len_vis_input=len_vis_input)
         encoded_layers = self.encoder(embedding_output, ext, prev_embedding=prev_embedding, prev_encoded_layers=prev_encoded_layers,
-                                      output_all_encoded_layers=output_all_encoded_layers)
+                                      output_all_encoded_layers=output_all_encoded_layers, kv_caches=kv_caches, cache_pos=cache_pos)
         sequence_output = encoded_layers[-1]
         pooled_output = self.pooler(sequence_output)
         if not output_all_encoded_layers:
@@ -635,7 +654,13 @@ class BertForSeq2SeqDecoder(PreTrainedBertModel, _RegionProjections):
         self.forbid_ignore_set = forbid_ignore_set
         self.ngram_size = ngram_size
         self.min_len = min_len
+        self.use_kv_cache = True     # False: the reference's data flow (K, V of the whole prefix re-projected at every step, modeling.py:273-277)
         self._build_region_projections(config, enable_butd)
+
+    def new_kv_caches(self, batch, device, rows=128):
+        """One [batch, rows, 2H] bf16 K|V cache per encoder layer."""
+        H = self.config.hidden_size
+        return [torch.empty(batch, rows, 2 * H, device=device, dtype=torch.bfloat16) for _ in self.bert.encoder.layer]
 
     def forward(self, vis_feats, vis_pe, input_ids, token_type_ids, position_ids, attention_mask, task_idx=None, sample_mode="greedy"):
         with torch.no_grad():
@@ -647,6 +672,7 @@ class BertForSeq2SeqDecoder(PreTrainedBertModel, _RegionProjections):
             output_length = token_type_ids.size(1)
             output_ids, output_probs = [], []
             prev_embedding, prev_encoded_layers = None, None
+            caches = self.new_kv_caches(input_ids.size(0), input_ids.device) if self.use_kv_cache else None
             curr_ids = input_ids
             mask_ids = input_ids[:, :1] * 0 + self.mask_word_id
             next_pos = input_length
@@ -654,10 +680,19 @@ class BertForSeq2SeqDecoder(PreTrainedBertModel, _RegionProjections):
                 curr_length = curr_ids.size(1)
                 start_pos = next_pos - curr_length
                 x_input_ids = torch.cat((curr_ids, mask_ids), dim=1)
-                new_embedding, new_encoded_layers, _ = self.bert(
-                    vis_feats, vis_pe, x_input_ids, token_type_ids[:, start_pos:next_pos + 1], position_ids[:, start_pos:next_pos + 1],
-                    attention_mask[:, start_pos:next_pos + 1, :next_pos + 1], prev_embedding=prev_embedding,
-                    prev_encoded_layers=prev_encoded_layers, output_all_encoded_layers=True, len_vis_input=self.len_vis_input)
+                if caches is not None:
+                    # rows [0, start_pos) of every layer's cache hold K|V of the real tokens decoded so far; this step appends
+                    # (new token, [MASK]) at [start_pos, next_pos] — the [MASK] row is overwritten by the next step's token
+                    new_embedding, new_encoded_layers, _ = self.bert(
+                        vis_feats, vis_pe, x_input_ids, token_type_ids[:, start_pos:next_pos + 1], position_ids[:, start_pos:next_pos + 1],
+                        attention_mask[:, start_pos:next_pos + 1, :next_pos + 1], output_all_encoded_layers=False,
+                        len_vis_input=self.len_vis_input, kv_caches=caches, cache_pos=start_pos)
+                    new_encoded_layers = [new_encoded_layers]
+                else:
+                    new_embedding, new_encoded_layers, _ = self.bert(
+                        vis_feats, vis_pe, x_input_ids, token_type_ids[:, start_pos:next_pos + 1], position_ids[:, start_pos:next_pos + 1],
+                        attention_mask[:, start_pos:next_pos + 1, :next_pos + 1], prev_embedding=prev_embedding,
+                        prev_encoded_layers=prev_encoded_layers, output_all_encoded_layers=True, len_vis_input=self.len_vis_input)
                 last_hidden = new_encoded_layers[-1][:, -1:, :]
                 prediction_scores, _ = self.cls(last_hidden, None, task_idx=task_idx)
                 if sample_mode == "greedy":
@@ -670,7 +705,9 @@ class BertForSeq2SeqDecoder(PreTrainedBertModel, _RegionProjections):
                     raise NotImplementedError
                 output_ids.append(max_ids)
                 output_probs.append(max_probs)
-                if prev_embedding is None:
+                if caches is not None:
+                    pass
+                elif prev_embedding is None:
                     prev_embedding = new_embedding[:, :-1, :]
                     prev_encoded_layers = [x[:, :-1, :] for x in new_encoded_layers]
                 else:
