@@ -95,6 +95,10 @@ def test_beam_search_matches_reference_traces(golden_dir):
             assert torch.equal(tr["ptrs"][b].cpu(), gold["ptrs"][b]) and torch.equal(tr["pred_seq"][b].cpu(), gold["pred_seq"][b])
         else:
             fr = t // gold["K"]
-            gs = gold["scores"][b, fr]
-            assert float((gs.max() - gs.min())) < 0.5 or True              # informational: flips happen between near-tied hypotheses
-            print(f"beam sample {b}: first differing word at frame {fr}; reference frame scores {gs.tolist()}")
+            gs = gold["scores"][b, fr].sort(descending=True).values
+            gaps = (gs[:-1] - gs[1:]).abs()
+            ours = tr["scores"][b, fr].float().cpu().sort(descending=True).values
+            # explained only if the frame holds a near-tie in the reference AND our hypothesis scores still match the reference's
+            assert float(gaps.min()) < MARGIN and float((ours - gs).abs().max()) < 2 * MARGIN, \
+                f"beam sample {b}: decisions differ at frame {fr} without a near-tie: reference {gs.tolist()} ours {ours.tolist()}"
+            print(f"beam sample {b}: first differing word at frame {fr}; reference frame scores {gs.tolist()} (near-tie)")

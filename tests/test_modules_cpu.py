@@ -249,13 +249,24 @@ def test_greedy_decode_marshalling_dry_run():
     mask = torch.zeros(B, L, L, dtype=torch.long)
     mask[:, :, :R + 2] = 1
     mask[:, R + 2:, R + 2:] = torch.tril(torch.ones(L - R - 2, L - R - 2, dtype=torch.long))
-    with abi_cases.dry_run() as calls:
-        ids, scores = model(torch.randn(B, R, d.vis_dim).bfloat16(), torch.randn(B, R, d.pe_dim).bfloat16(), input_ids, tt, pos, mask,
-                            task_idx=None, sample_mode="greedy")
     steps = L - R - 2
+    vis, pe = torch.randn(B, R, d.vis_dim).bfloat16(), torch.randn(B, R, d.pe_dim).bfloat16()
+    with abi_cases.dry_run() as calls:                       # default: per-layer K/V caches, one vlpk_layer_cached_fwd per layer and step
+        ids, scores = model(vis, pe, input_ids, tt, pos, mask, task_idx=None, sample_mode="greedy")
+    assert ids.shape == (B, steps) and model.use_kv_cache
+    assert calls.count("vlpk_layer_cached_fwd") == steps * cfg.num_hidden_layers and "vlpk_layer_fwd" not in calls
+    assert calls.count("vlpk_embed_fwd") == steps and "vlpk_encoder_bwd" not in calls
+    model.use_kv_cache = False                               # the reference's data flow: prefix re-encoded through vlpk_layer_fwd
+    with abi_cases.dry_run() as calls:
+        ids, scores = model(vis, pe, input_ids, tt, pos, mask, task_idx=None, sample_mode="greedy")
     assert ids.shape == (B, steps)
     assert calls.count("vlpk_layer_fwd") + calls.count("vlpk_encoder_fwd") * cfg.num_hidden_layers >= steps * cfg.num_hidden_layers
-    assert calls.count("vlpk_embed_fwd") == steps and "vlpk_encoder_bwd" not in calls
+    assert calls.count("vlpk_embed_fwd") == steps and "vlpk_layer_cached_fwd" not in calls
+    model.search_beam_size, model.use_kv_cache = 3, True     # beam search over the caches: traces of the reference's format
+    with abi_cases.dry_run() as calls:
+        tr = model(vis, pe, input_ids, tt, pos, mask, task_idx=None)
+    assert set(tr) == {"pred_seq", "scores", "wids", "ptrs"} and tr["pred_seq"].shape == (B, L) and tr["wids"].shape == (B, L, 3)
+    assert calls.count("vlpk_layer_cached_fwd") == steps * cfg.num_hidden_layers
 
 
 # ---------------------------------------------------------------------------------------------------------------------------
