@@ -207,6 +207,7 @@ def main():
     ap.add_argument("--config", default="caption", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the optimizer-inclusive, exposed-communication and profile passes")
+    ap.add_argument("--no-graph", action="store_true", help="drive every step from Python instead of replaying the captured CUDA graph (N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -261,15 +262,21 @@ def main():
             opt.step()
         return loss
 
-    def timed_loop(n, opt=None):
-        """n steps on the device-resident batch; returns (total ms, sorted per-step ms) from one CUDA event per step."""
+    def timed_loop(n, opt=None, graphed=None):
+        """n steps on the device-resident batch; returns (total ms, sorted per-step ms) from one CUDA event per step.
+        graphed: a vlp_b200.graph.GraphedStep replayed instead of the Python-driven step (same kernels, same work)."""
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         torch.cuda.synchronize()
         barrier()
         torch.cuda.synchronize()
         evs[0].record()
         for i in range(n):
-            one_step(dev_batch, opt)
+            if graphed is not None:
+                graphed()
+                if opt is not None:
+                    opt.step()
+            else:
+                one_step(dev_batch, opt)
             evs[i + 1].record()
         torch.cuda.synchronize()
         barrier()
@@ -319,10 +326,43 @@ def main():
         for _ in range(2):
             one_step(dev_batch)
 
+    # The step (forward + backward + the reducer's collectives when N > 1) is captured once as a CUDA graph and replayed
+    # (vlp_b200.graph; same kernels, fresh dropout masks per replay): Python needs ~6 ms per step to enqueue the ~330 launches, and
+    # with N processes sharing the host it becomes the bottleneck (2 GPUs: 7.14 ms per step even with the all-reduce switched off).
+    # torch-DDP runs (VLP_BENCH_DP=torch_ddp) and VLP_BENCH_GRAPH=0 stay Python-driven.
+    use_graph = (not args.no_graph) and os.environ.get("VLP_BENCH_GRAPH", "1") != "0" and (world == 1 or reducer is not None)
+    gstep = None
+
+    def graph_body(m, b):
+        loss = step_fn(m, b, tasks)
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    cap_mode = "global" if world == 1 else "thread_local"
+    if use_graph:
+        from vlp_b200.graph import GraphedStep
+        if world > 1:
+            torch.cuda.synchronize()
+            barrier()
+            time.sleep(0.5)          # let torch.distributed's watchdog retire the warm-up collectives before the capture starts
+        gstep = GraphedStep(net, dev_batch, graph_body, capture_error_mode=cap_mode)
+        for _ in range(2):
+            gstep()
     launches0 = L.lib().vlpk_launch_count()
     with ClockSampler(local_rank) as clocks:
-        ms_total, per_step = timed_loop(args.steps)
-    launches = L.lib().vlpk_launch_count() - launches0
+        ms_total, per_step = timed_loop(args.steps, graphed=gstep)
+    launches = (gstep.launches_per_replay * args.steps) if gstep is not None else (L.lib().vlpk_launch_count() - launches0)
+    eager = None
+    if gstep is not None and not args.no_extras:
+        # the same loop driven from Python, for reference (host enqueue ~ device time: any host hiccup shows up here)
+        n_e = min(args.steps, 30)
+        for _ in range(2):
+            one_step(dev_batch)
+        ms_e, _ = timed_loop(n_e)
+        ms_e = max_over_ranks(ms_e)
+        eager = {"value": B * world * n_e / (ms_e / 1e3), "unit": "samples/s", "ms_per_step": ms_e / n_e,
+                 "what": "same step, Python-driven launches (no graph)"}
     ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total / 1e3)
@@ -346,13 +386,19 @@ def main():
         stager.get().done()
     n_e2e = args.steps if args.steps <= 200 else 200
     loss_host = torch.zeros(n_e2e + warmup, dtype=torch.float32).pin_memory()
+    g_e2e = None
+    if use_graph:
+        stager.put(stager.slot(fields))
+        b0 = stager.get()
+        g_e2e = GraphedStep(net, b0, graph_body, capture_error_mode=cap_mode)     # captured on the staged batch format (packed mask)
+        b0.done()
 
     def e2e_step(i):
         if i == 0:
             stager.put(stager.slot(fields))
         b = stager.get()
         stager.put(stager.slot(fields))                 # next batch's copies overlap this step's compute
-        loss = one_step(b)
+        loss = g_e2e(b) if g_e2e is not None else one_step(b)
         b.done()
         loss_host[i].copy_(loss.detach().float().reshape(()), non_blocking=True)
 
@@ -386,9 +432,17 @@ def main():
                   {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]   # run_img2txt_dist.py:394-401
         opt = BertAdam(groups, lr=3e-5, warmup=0.1, t_total=100000)
         n_opt = min(args.steps, 30)
-        for _ in range(3):
-            one_step(dev_batch, opt)
-        ms_opt, _ = timed_loop(n_opt, opt)
+        g_opt = None
+        if use_graph:
+            g_opt = GraphedStep(net, dev_batch, graph_body, capture_error_mode=cap_mode)   # p.grad = this capture's static gradient tensors
+            for _ in range(3):
+                g_opt()
+                opt.step()
+        else:
+            for _ in range(3):
+                one_step(dev_batch, opt)
+        ms_opt, _ = timed_loop(n_opt, opt, graphed=g_opt)
+        g_opt = None
         ms_opt = max_over_ranks(ms_opt) / n_opt
         extras["optimizer"] = {"value": B * world / (ms_opt / 1e3), "unit": "samples/s", "ms_per_step": ms_opt,
                                "optimizer_ms": ms_opt - ms_per_step,
@@ -396,9 +450,11 @@ def main():
                                        "weights and moments, per-tensor clipping (optimization.py:112-182)"}
         if reducer is not None:
             reducer.enabled = False
+            g_nc = GraphedStep(net, dev_batch, graph_body, capture_error_mode=cap_mode) if use_graph else None
             for _ in range(2):
-                one_step(dev_batch)
-            ms_nocomm, _ = timed_loop(min(args.steps, 30))
+                g_nc() if g_nc is not None else one_step(dev_batch)
+            ms_nocomm, _ = timed_loop(min(args.steps, 30), graphed=g_nc)
+            g_nc = None
             reducer.enabled = True
             ms_nocomm = max_over_ranks(ms_nocomm) / min(args.steps, 30)
             extras["comm"] = {"exposed_ms_per_step": ms_per_step - ms_nocomm, "ms_per_step_without_allreduce": ms_nocomm,
@@ -445,6 +501,12 @@ def main():
     peak_tf = peaks["bf16_tflops_sustained"] if capped else peaks["bf16_tflops"]
     fl = synth.flops_per_sample(tasks=tasks)
     step_tf = value / world * fl["total"] / 1e12
+    # algorithmic HBM bytes per step of the bandwidth-bound kernels: LN as counted by the library (3 / 5 arrays of [M,H] bf16); attention
+    # core fwd = qkv read + ctx write + keep-bits write, bwd = qkv + dctx read + dqkv write + keep-bits read (the library counts FLOPs there)
+    Mrows, Hh, nl = B * d.seq_len, d.hidden, d.layers
+    keep_b = B * d.heads * d.seq_len * 16
+    hbm_bytes = {"ln_fwd": prof["ln_fwd"]["work_per_step"], "ln_bwd": prof["ln_bwd"]["work_per_step"],
+                 "attn_fwd": nl * (Mrows * Hh * 2 * 4 + keep_b), "attn_bwd": nl * (Mrows * Hh * 2 * 7 + keep_b)}
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if os.path.exists(tp):
@@ -459,9 +521,10 @@ def main():
                 "whole_step": {"achieved": step_tf, "frac": step_tf / peak_tf, "flops_per_sample": fl["total"]},
                 "families_ms_per_step": {n: round(prof[n]["ms_per_step"], 4) for n in names},
                 "families_note": "CUDA events around every launch of one profiled step, side-stream overlap disabled for this pass",
-                "hbm_kernels": {n: {"GBps": (prof[n]["work_per_step"] / (prof[n]["ms_per_step"] * 1e-3) / 1e9 if prof[n]["ms_per_step"] > 0 else 0.0),
-                                    "frac_of_hbm_peak": (prof[n]["work_per_step"] / (prof[n]["ms_per_step"] * 1e-3) / 1e9 / peaks["hbm_gbs"]
-                                                         if prof[n]["ms_per_step"] > 0 else 0.0)} for n in ("ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd")}}
+                "hbm_kernels": {n: {"GBps": (hbm_bytes[n] / (prof[n]["ms_per_step"] * 1e-3) / 1e9 if prof[n]["ms_per_step"] > 0 else 0.0),
+                                    "frac_of_hbm_peak": (hbm_bytes[n] / (prof[n]["ms_per_step"] * 1e-3) / 1e9 / peaks["hbm_gbs"]
+                                                         if prof[n]["ms_per_step"] > 0 else 0.0),
+                                    "algorithmic_bytes_per_step": hbm_bytes[n]} for n in ("ln_fwd", "ln_bwd", "attn_fwd", "attn_bwd")}}
     n10 = max(1, args.steps // 10)
     step_stats.pop("first_tenth_mean_ms"), step_stats.pop("last_tenth_mean_ms")
     line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
@@ -470,7 +533,9 @@ def main():
                        "parallelism": f"dp{world}" + ("" if world == 1 else (" torch-DDP" if reducer is None else
                                                                                " NCCL all-reduce of flat bf16 gradient arenas overlapped with backward")),
                        "l2": "per-step working set (2.3 GB saved activations + 0.23 GB weights) is far larger than the 126 MB L2; no explicit flush",
-                       "timing": "CUDA events on the launch stream (one per step), barrier + synchronize both sides, max over ranks"},
+                       "timing": "CUDA events on the launch stream (one per step), barrier + synchronize both sides, max over ranks",
+                       "launch": ("CUDA-graph replay of the captured step (vlp_b200.graph.GraphedStep): identical kernels, device-side seed counter "
+                                  "bumped per replay for fresh dropout masks" if use_graph else "Python-driven launches")},
             "step_ms": step_stats,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "steps": n_e2e,
                     "host_enqueue_ms": {"p50": round(pct(host_ms, 0.5), 3), "p95": round(pct(host_ms, 0.95), 3), "max": round(host_ms[-1], 3)},
@@ -479,6 +544,8 @@ def main():
                            "pinned host memory; host wall clock around the loop"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clk, "final_loss": final_loss}
     line.update(extras)
+    if eager is not None:
+        line["eager"] = eager
     if world == 1 and not args.no_cpu_baseline:
         res = cpu_reference_run(args.config, batch=8, warmup=1, steps=2)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
