@@ -330,7 +330,8 @@ def main():
     # (vlp_b200.graph; same kernels, fresh dropout masks per replay): Python needs ~6 ms per step to enqueue the ~330 launches, and
     # with N processes sharing the host it becomes the bottleneck (2 GPUs: 7.14 ms per step even with the all-reduce switched off).
     # torch-DDP runs (VLP_BENCH_DP=torch_ddp) and VLP_BENCH_GRAPH=0 stay Python-driven.
-    use_graph = (not args.no_graph) and os.environ.get("VLP_BENCH_GRAPH", "1") != "0" and (world == 1 or reducer is not None)
+    use_graph = (not args.no_graph) and os.environ.get("VLP_BENCH_GRAPH", "1") != "0" and \
+        (world == 1 or (reducer is not None and os.environ.get("VLP_BENCH_GRAPH_DP", "0") == "1"))
     gstep = None
 
     def graph_body(m, b):
