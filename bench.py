@@ -331,7 +331,7 @@ def main():
     # with N processes sharing the host it becomes the bottleneck (2 GPUs: 7.14 ms per step even with the all-reduce switched off).
     # torch-DDP runs (VLP_BENCH_DP=torch_ddp) and VLP_BENCH_GRAPH=0 stay Python-driven.
     use_graph = (not args.no_graph) and os.environ.get("VLP_BENCH_GRAPH", "1") != "0" and \
-        (world == 1 or (reducer is not None and os.environ.get("VLP_BENCH_GRAPH_DP", "0") == "1"))
+        (world == 1 or (reducer is not None and os.environ.get("VLP_BENCH_GRAPH_DP", "1") == "1"))
     gstep = None
 
     def graph_body(m, b):
@@ -486,9 +486,21 @@ def main():
         torch.cuda.synchronize()
     barrier()
 
+    def shutdown():
+        """Leave the process group.  With captured graphs alive, tearing NCCL down (destroy_process_group) blocked for minutes after the
+        result line had been printed (2-GPU run, round 2): the graphs hold the communicator's kernels.  The benchmark is done at this
+        point, so the ranks synchronise, flush and exit directly."""
+        if world == 1:
+            return
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if use_graph:
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     peaks = load_peaks()
@@ -551,8 +563,7 @@ def main():
         res = cpu_reference_run(args.config, batch=8, warmup=1, steps=2)
         line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":
