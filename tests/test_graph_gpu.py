@@ -85,3 +85,28 @@ def test_replays_draw_fresh_dropout_masks():
                     masked_pos=b0["masked_pos"], masked_weights=b0["masked_weights"], task_idx=b0["task_idx"], drop_worst_ratio=0.0)
     ref = float(out[0] + out[1] + out[2])
     assert all(abs(x - ref) < 0.5 for x in losses), (losses, ref)
+
+
+@pytest.mark.parametrize("K", [1, 3])
+def test_graphed_decode_equals_python_driven_decode(K):
+    """The whole decode loop (region projections, 21 K/V-cache steps, arg-max or beam bookkeeping + back-tracking) replayed as one graph
+    gives the ids / scores of the Python-driven loop, also for inputs other than the captured ones."""
+    from test_decode_gpu import _decoder, _inputs
+    d = synth.SMALL_L123
+    model = _decoder(d, K)
+
+    def args(seed):
+        vis, pe, input_ids, tt, pos, mask = _inputs(d, 3, seed)
+        return (vis.cuda().bfloat16(), pe.cuda().bfloat16(), input_ids.cuda(), tt.cuda(), pos.cuda(), mask.cuda())
+
+    a0, a1 = args(5), args(6)
+    g = graph.GraphedCall(lambda *a: model(*a, task_idx=None), a0)
+    assert g.launches_per_replay > 100
+    for a in (a1, a0):
+        want = model(*a, task_idx=None)
+        got = g(*a)
+        if K == 1:
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        else:
+            for k in ("pred_seq", "wids", "ptrs", "scores"):
+                assert torch.equal(got[k], want[k]), k

@@ -79,3 +79,40 @@ class GraphedStep:
         self._seed.add_(1)                               # fresh dropout masks from the frozen launch sequence
         self.graph.replay()
         return self.loss
+
+
+class GraphedCall:
+    """Capture `fn(*tensors)` (inference: no autograd, no host synchronisation, fixed shapes) once and replay it.
+
+        dec = GraphedCall(lambda *a: decoder(*a, task_idx=None), (vis_feats, vis_pe, input_ids, token_type_ids, position_ids, mask))
+        ids, scores = dec(vis_feats2, vis_pe2, input_ids2, ...)        # copies into the captured inputs, replays, returns static outputs
+
+    Written for decode (`BertForSeq2SeqDecoder.forward`, modeling.py:1189-1253 / beam search :1256-1494): with the per-layer K/V caches a
+    decode step touches 2 new rows per sequence and is launch-bound (12 layers x 6 launches + head per step, 21 steps); every step has its
+    own shapes but the sequence of steps is fixed for a given (batch, lengths), so the whole loop — region projections, 21 cached decode
+    steps, greedy arg-max or beam bookkeeping and back-tracking, all on the device — is one graph.  The returned tensors are overwritten by
+    the next call; clone what must survive.  Not for `forbid_duplicate_ngrams` (host-side n-gram bookkeeping)."""
+
+    def __init__(self, fn, example_args, warmup=2):
+        self.static = tuple(a.clone() if torch.is_tensor(a) else a for a in example_args)
+        dev = next(a.device for a in self.static if torch.is_tensor(a))
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(max(1, warmup)):
+                fn(*self.static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = L.lib().vlpk_launch_count()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = fn(*self.static)
+        self.launches_per_replay = int(L.lib().vlpk_launch_count() - n0)
+
+    def __call__(self, *args):
+        for dst, src in zip(self.static, args):
+            if torch.is_tensor(dst) and src.data_ptr() != dst.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out
