@@ -11,7 +11,9 @@ scaling).  One step = one batch per GPU.
   ccmix   (configs[4])                : batch 64 per GPU, per-sample Bernoulli(0.75 seq2seq / 0.25 bidirectional) mask; run with
                                         --steps 2000 for the sustained-throughput protocol (per-step p5 / p95, clock / power trace)
 
-  value : samples/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.
+  value : samples/s, inputs resident in HBM, device-timed (CUDA events), max over ranks.  The step is captured once as a CUDA graph
+          (vlp_b200.graph.GraphedStep: forward + backward + the reducer's collectives, identical kernels, fresh dropout masks per
+          replay) and replayed; `eager` in the JSON line is the same loop driven from Python (--no-graph / VLP_BENCH_GRAPH=0: only that).
   e2e   : same metric through the product's staging API (vlp_b200.staging.BatchStager) with HOST buffers: every step's batch goes
           pinned host memory -> device (bf16 features + 3 integers per sample for the mask, double-buffered on a copy stream) and the
           loss is read back to the host, all inside the timed region (host wall clock).
