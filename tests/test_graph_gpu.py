@@ -65,6 +65,12 @@ def test_replay_equals_python_driven_step(packed):
         # same kernels, same inputs; only fp32 atomic accumulation order (bias / LayerNorm gradients, split-K weight gradients) may differ
         err = float((got[n] - want[n]).norm() / (want[n].norm() + 1e-30))
         assert err < 2e-3, (n, err)
+    # a training loop's zero_grad(set_to_none=True) between replays must not detach the captured gradient tensors
+    model.zero_grad(set_to_none=True)
+    g(b1)
+    again = _grads(model)
+    assert set(again) == set(want) and all(torch.equal(again[n], got[n]) or float((again[n] - got[n]).norm() / (got[n].norm() + 1e-30)) < 2e-3
+                                            for n in want)
     # a second replay on the first batch reproduces that batch's eager result too (inputs really are re-read)
     model2_loss = float(g(b0))
     model.zero_grad(set_to_none=True)

@@ -61,6 +61,9 @@ class GraphedStep:
         self.launches_per_replay = int(L.lib().vlpk_launch_count() - n0)   # libvlpk kernels inside one replay (torch's are extra)
         if self.launches_per_replay <= 0:
             raise RuntimeError("vlp_b200.graph: the captured step launched no libvlpk kernel")
+        # the gradient tensors the graph writes; re-attached after every replay so that a training loop's `optimizer.zero_grad()`
+        # (set_to_none=True, run_img2txt_dist.py's loop calls it every step) or an interleaved eager step cannot detach them
+        self._grads = [(p, p.grad) for p in model.parameters() if p.grad is not None]
 
     def load(self, batch):
         """Copy a device batch into the captured input buffers (async, on the current stream)."""
@@ -78,6 +81,9 @@ class GraphedStep:
             self.load(batch)
         self._seed.add_(1)                               # fresh dropout masks from the frozen launch sequence
         self.graph.replay()
+        for p, g in self._grads:
+            if p.grad is not g:
+                p.grad = g
         return self.loss
 
 
