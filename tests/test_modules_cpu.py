@@ -464,3 +464,19 @@ def test_encoder_layer_groups_dry_run():
     enc.layers_per_call = [2, 2]
     with pytest.raises(ValueError), abi_cases.dry_run():
         enc(x, mask)
+
+
+def test_mask_bits_cache_follows_in_place_edits():
+    """The packed form of an attention mask is cached on the tensor for the 12 layers of a forward, keyed by the tensor's in-place version:
+    the same tensor is packed once, an in-place edit is packed again (the cache went stale)."""
+    from tools import abi_cases
+    m = torch.zeros(2, 1, 12, 12)
+    with abi_cases.dry_run() as calls:
+        vm._mask_bits(m)
+        vm._mask_bits(m)
+        assert calls == ["vlpk_mask_pack"]
+        m[:, :, :, 6:] = -10000.0
+        vm._mask_bits(m)
+        assert calls == ["vlpk_mask_pack"] * 2
+        vm._mask_bits(m)
+        assert calls == ["vlpk_mask_pack"] * 2

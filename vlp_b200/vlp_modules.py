@@ -189,16 +189,28 @@ class BertOutput(nn.Module):
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
 
 
+def _tensor_version(t):
+    """Autograd's in-place version counter of a tensor (None where it is not tracked: inference tensors, non-tensors)."""
+    try:
+        return t._version
+    except Exception:
+        return None
+
+
 def _mask_bits(attention_mask):
     """Additive [B,1,R,KV] mask (get_extended_attention_mask) -> packed bits, cached on the tensor object so the
-    12 layers of one forward (and BertLayer calls made one by one) pack it once."""
+    12 layers of one forward (and BertLayer calls made one by one) pack it once.  The cache is keyed by the tensor's
+    in-place version counter: a mask edited in place after it was packed is packed again."""
     bits = getattr(attention_mask, "_vlpk_bits", None)
-    if bits is None:
-        bits = ops.pack_mask(attention_mask, "additive")
-        try:
-            attention_mask._vlpk_bits = bits
-        except Exception:  # pragma: no cover
-            pass
+    if bits is not None and (not torch.is_tensor(attention_mask)
+                             or getattr(attention_mask, "_vlpk_bits_version", None) == _tensor_version(attention_mask)):
+        return bits
+    bits = ops.pack_mask(attention_mask, "additive")
+    try:
+        attention_mask._vlpk_bits = bits
+        attention_mask._vlpk_bits_version = _tensor_version(attention_mask)
+    except Exception:  # pragma: no cover
+        pass
     return bits
 
 
@@ -463,6 +475,7 @@ class BertModel(PreTrainedBertModel):
         if attention_mask.is_cuda:
             src = attention_mask if attention_mask.dtype in (torch.int64, torch.float32, torch.bfloat16) else attention_mask.float()
             ext._vlpk_bits = ops.pack_mask(src, "zero_one")
+            ext._vlpk_bits_version = _tensor_version(ext)
         return ext
 
     def forward(self, vis_feats, vis_pe, input_ids, token_type_ids=None, attention_mask=None, output_all_encoded_layers=True, len_vis_input=49):
